@@ -1,0 +1,297 @@
+// Library plumbing + device-wide primitives (fill, exclusive scan, stable LSD radix sort).
+// These replace the library calls the reference leans on for the same jobs: torch::full / torch::zeros
+// (spconv_ops.h:55-62), torch::_unique's thrust sort (spconv_ops.h:126) and torch_scatter's atomics.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace wsis {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_i32_kernel(int32_t *__restrict__ dst, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // 16-byte stores on the aligned body
+  int64_t n4 = n / 4;
+  int4 v4 = make_int4(v, v, v, v);
+  int4 *d4 = reinterpret_cast<int4 *>(dst);
+  for (int64_t j = i; j < n4; j += stride) d4[j] = v4;
+  for (int64_t j = n4 * 4 + i; j < n; j += stride) dst[j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan: 256 threads x 8 items per block
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *smem /*>=9 ints*/) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = lane < (kScanThreads / 32) ? smem[lane] : 0;
+    int xi = x;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (lane >= o) xi += t;
+    }
+    if (lane < 8) smem[lane] = xi - x;
+    if (lane == 7) smem[8] = xi;
+  }
+  __syncthreads();
+  int res = smem[w] + inc - v;
+  *total = smem[8];
+  __syncthreads();
+  return res;
+}
+
+__global__ void scan_block_sums(const int32_t *__restrict__ in, int64_t n, int32_t *__restrict__ bsum) {
+  __shared__ int sm[9];
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+    if (base + j < n) s += in[base + j];
+  int total;
+  block_exclusive_scan(s, &total, sm);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void scan_bsums(int32_t *bsum, int nb) {
+  __shared__ int sm[9];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += kScanThreads) {
+    int i = base + threadIdx.x;
+    int v = i < nb ? bsum[i] : 0;
+    int total;
+    int ex = block_exclusive_scan(v, &total, sm);
+    if (i < nb) bsum[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bsum[nb] = carry;
+}
+
+__global__ void scan_apply(const int32_t *in, int32_t *out, int64_t n, const int32_t *__restrict__ bsum, int nb) {
+  __shared__ int sm[9];
+  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  int v[kScanItems];
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    v[j] = (base + j < n) ? in[base + j] : 0;
+    s += v[j];
+  }
+  int total;
+  int ex = block_exclusive_scan(s, &total, sm) + bsum[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    if (base + j < n) out[base + j] = ex;
+    ex += v[j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = bsum[nb];
+}
+
+static int launch_scan(const int32_t *in, int32_t *out, int64_t n, void *ws, cudaStream_t st) {
+  WSIS_CHECK(n >= 0 && n < (int64_t)1 << 31, "scan: n=%lld out of range", (long long)n);
+  int32_t *bsum = reinterpret_cast<int32_t *>(ws);
+  if (n == 0) {
+    WSIS_CUDA(cudaMemsetAsync(out, 0, sizeof(int32_t), st));
+    return 0;
+  }
+  int nb = (int)ceil_div(n, kScanTile);
+  scan_block_sums<<<nb, kScanThreads, 0, st>>>(in, n, bsum);
+  WSIS_LAUNCH_OK();
+  scan_bsums<<<1, kScanThreads, 0, st>>>(bsum, nb);
+  WSIS_LAUNCH_OK();
+  scan_apply<<<nb, kScanThreads, 0, st>>>(in, out, n, bsum, nb);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stable LSD radix sort, 8 bits per pass, (u32 key, u32 value)
+// ------------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortRounds = 8;
+constexpr int kSortTile = kSortThreads * kSortRounds;
+
+__global__ void sort_hist(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t mask,
+                          int32_t *__restrict__ hist, int nb) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortRounds; ++r) {
+    int64_t i = base + r * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & mask], 1);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void sort_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                             uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+                             uint32_t mask, const int32_t *__restrict__ hist_scanned, int nb) {
+  __shared__ int running[256];
+  __shared__ int cnt[kSortThreads / 32][256];
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  running[t] = hist_scanned[(int64_t)t * nb + blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+  for (int r = 0; r < kSortRounds; ++r) {
+#pragma unroll
+    for (int ww = 0; ww < kSortThreads / 32; ++ww) cnt[ww][t] = 0;
+    __syncthreads();
+    int64_t i = base + r * kSortThreads + t;
+    bool valid = i < n;
+    uint32_t key = valid ? keys_in[i] : 0u;
+    uint32_t val = valid ? vals_in[i] : 0u;
+    uint32_t d = (key >> shift) & mask;
+    uint32_t dd = valid ? d : (0x10000u + (uint32_t)lane);
+    unsigned m = __match_any_sync(0xffffffffu, dd);
+    int rank = __popc(m & ((1u << lane) - 1u));
+    if (valid && rank == 0) cnt[w][d] = __popc(m);
+    __syncthreads();
+    {
+      int run = running[t];
+#pragma unroll
+      for (int ww = 0; ww < kSortThreads / 32; ++ww) {
+        int c = cnt[ww][t];
+        cnt[ww][t] = run;
+        run += c;
+      }
+      running[t] = run;
+    }
+    __syncthreads();
+    if (valid) {
+      int pos = cnt[w][d] + rank;
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace wsis
+
+using namespace wsis;
+
+extern "C" {
+
+int wsis_version(void) { return 100; }
+const char *wsis_last_error(void) { return g_err; }
+int64_t wsis_launch_count(void) { return g_launches.load(); }
+
+int wsis_device_info(int *sms, int *major, int *minor) {
+  int dev = 0;
+  WSIS_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  WSIS_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sms) *sms = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  return 0;
+}
+
+int wsis_fill_i32(int32_t *dst, int64_t n, int32_t value, wsis_stream_t stream) {
+  if (n <= 0) return 0;
+  WSIS_CHECK((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "fill: dst must be 16-byte aligned");
+  int blocks = (int)std::min<int64_t>(ceil_div(n, 256 * 4 * 4), (int64_t)sm_count() * 8);
+  fill_i32_kernel<<<std::max(blocks, 1), 256, 0, as_stream(stream)>>>(dst, n, value);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int64_t wsis_scan_ws_bytes(int64_t n) { return (ceil_div(n > 0 ? n : 1, kScanTile) + 2) * (int64_t)sizeof(int32_t); }
+
+int wsis_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, void *ws, wsis_stream_t stream) {
+  return launch_scan(in, out, n, ws, as_stream(stream));
+}
+
+static inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+
+int64_t wsis_sort_ws_bytes(int64_t n) {
+  int64_t nb = ceil_div(n > 0 ? n : 1, kSortTile);
+  return 2 * align256(n * 4) + align256((256 * nb + 1) * 4) + align256(wsis_scan_ws_bytes(256 * nb));
+}
+
+int wsis_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+                        int64_t n, int begin_bit, int end_bit, void *ws, wsis_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  WSIS_CHECK(n >= 0 && n < ((int64_t)1 << 31), "sort: n out of range");
+  WSIS_CHECK(begin_bit >= 0 && end_bit <= 32 && begin_bit <= end_bit, "sort: bad bit range");
+  if (n == 0) return 0;
+  int passes = (end_bit - begin_bit + 7) / 8;
+  if (passes == 0) {
+    WSIS_CUDA(cudaMemcpyAsync(keys_out, keys_in, n * 4, cudaMemcpyDeviceToDevice, st));
+    WSIS_CUDA(cudaMemcpyAsync(vals_out, vals_in, n * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  int nb = (int)ceil_div(n, kSortTile);
+  char *p = reinterpret_cast<char *>(ws);
+  uint32_t *tk = reinterpret_cast<uint32_t *>(p);
+  p += align256(n * 4);
+  uint32_t *tv = reinterpret_cast<uint32_t *>(p);
+  p += align256(n * 4);
+  int32_t *hist = reinterpret_cast<int32_t *>(p);
+  p += align256((256 * (int64_t)nb + 1) * 4);
+  void *scan_ws = p;
+  const uint32_t *sk = keys_in, *sv = vals_in;
+  for (int ps = 0; ps < passes; ++ps) {
+    int shift = begin_bit + 8 * ps;
+    int bits = std::min(8, end_bit - shift);
+    uint32_t mask = (1u << bits) - 1u;
+    bool to_out = ((passes - 1 - ps) % 2) == 0;
+    uint32_t *dk = to_out ? keys_out : tk, *dv = to_out ? vals_out : tv;
+    sort_hist<<<nb, kSortThreads, 0, st>>>(sk, n, shift, mask, hist, nb);
+    WSIS_LAUNCH_OK();
+    if (launch_scan(hist, hist, 256 * (int64_t)nb, scan_ws, st)) return 1;
+    sort_scatter<<<nb, kSortThreads, 0, st>>>(sk, sv, dk, dv, n, shift, mask, hist, nb);
+    WSIS_LAUNCH_OK();
+    sk = dk;
+    sv = dv;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+"""Tensor-level host wrappers over the C ABI (include/wsis_b200.h).
+
+PyTorch is only the allocator / stream provider here: every function takes torch tensors, allocates outputs
+and workspaces with torch, and hands raw device pointers + the current CUDA stream to the library.  Nothing
+in this file computes on the CPU; a CPU tensor where a CUDA tensor is required raises.
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from ._lib import lib
+
+# ---------------------------------------------------------------------------------------------------------
+# configuration
+# ---------------------------------------------------------------------------------------------------------
+# "fp32": tcgen05 with bf16x3 split operands (fp32 contract, 1e-4); "bf16": tcgen05 with bf16 operands (1e-2);
+# "simt": exact fp32 FFMA kernel everywhere.  Layers the tensor-core kernel cannot take (Cin % 32 != 0, e.g. the
+# 6->32 input conv) always run on the SIMT kernel.
+_PRECISION = os.environ.get("WSIS_PRECISION", "fp32")
+
+
+def set_precision(p):
+    global _PRECISION
+    assert p in ("fp32", "bf16", "simt"), p
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _i3(v):
+    if not isinstance(v, (list, tuple)):
+        v = [v] * 3
+    v = [int(x) for x in v]
+    assert len(v) == 3, "only 3-D sparse convolutions are supported"
+    return v
+
+
+def _c3(v):
+    return (ctypes.c_int32 * 3)(*v)
+
+
+def _cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("wsis_b200: %s must be a CUDA tensor (there is no CPU path for this op)" % name)
+    return t
+
+
+def _bytes(n, device):
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=device)
+
+
+def launch_count():
+    return int(lib().value("wsis_launch_count"))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# rulebook
+# ---------------------------------------------------------------------------------------------------------
+class Rulebook:
+    """Output-stationary rulebook: nbr_in[i,k] = out row, nbr_out[o,k] = in row (see include/wsis_b200.h).
+
+    Replaces the (indice_pairs, indice_pair_num) pair of spconv_ops.h:27-137; `pairs()` still materialises the
+    reference-format tensors (conv.py:152 stores them in indice_dict)."""
+
+    def __init__(self, kind, K, n_in, n_out, nbr_in, nbr_out, out_coords):
+        self.kind, self.K, self.n_in, self.n_out = kind, K, n_in, n_out
+        self.nbr_in, self.nbr_out, self.out_coords = nbr_in, nbr_out, out_coords
+        self._pairs = None
+
+    def pairs(self):
+        if self._pairs is None:
+            dev = self.nbr_in.device
+            N, K = self.n_in, self.K
+            pairs = torch.empty((K, 2, N), dtype=torch.int32, device=dev)
+            num = torch.empty((K,), dtype=torch.int32, device=dev)
+            if N > 0:
+                pos = torch.empty((K * N + 1,), dtype=torch.int32, device=dev)
+                ws = _bytes(lib().value("wsis_scan_ws_bytes", K * N), dev)
+                lib().call("wsis_pairs_from_nbr", _ptr(self.nbr_in), N, K, _ptr(pairs), _ptr(num), _ptr(pos), _ptr(ws),
+                           _stream())
+            else:
+                num.zero_()
+            self._pairs = (pairs, num)
+        return self._pairs
+
+    # (map, flip) for: y[dst] = sum_k x[map[dst,k]] W[k]
+    def fwd_map(self):
+        return (self.nbr_in, 1) if self.kind == "subm" else (self.nbr_out, 0)
+
+    def bwd_map(self):  # maps rows of the conv INPUT side to rows of the OUTPUT side
+        return (self.nbr_in, 0)
+
+
+def rulebook_subm(indices, spatial_shape, ksize=3, dilation=1):
+    """Submanifold rulebook: replaces getIndicePair<3> with subM=1 (spconv_ops.h:86-102)."""
+    indices = _cuda(indices, "indices")
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4
+    indices = indices.contiguous()
+    ks, dil, shape = _i3(ksize), _i3(dilation), _i3(list(spatial_shape))
+    K = ks[0] * ks[1] * ks[2]
+    N = indices.shape[0]
+    dev = indices.device
+    nbr = torch.empty((N, K), dtype=torch.int32, device=dev)
+    if N > 0:
+        slots = lib().value("wsis_hash_slots", N)
+        keys = torch.empty((slots,), dtype=torch.int64, device=dev)
+        vals = torch.empty((slots,), dtype=torch.int32, device=dev)
+        lib().call("wsis_rulebook_subm", _ptr(indices), N, _c3(ks), _c3(dil), _c3(shape), _ptr(keys), _ptr(vals), slots,
+                   _ptr(nbr), _stream())
+    return Rulebook("subm", K, N, N, nbr, None, indices)
+
+
+def conv_output_shape(spatial_shape, ksize, stride, padding, dilation):
+    """ops.get_conv_output_size, spconv/ops.py:19-30."""
+    s, k, st, p, d = _i3(list(spatial_shape)), _i3(ksize), _i3(stride), _i3(padding), _i3(dilation)
+    return [(s[i] + 2 * p[i] - d[i] * (k[i] - 1) - 1) // st[i] + 1 for i in range(3)]
+
+
+def rulebook_conv(indices, spatial_shape, ksize, stride, padding=0, dilation=1):
+    """Strided sparse-conv rulebook: replaces getIndicePair<3> with subM=0 (spconv_ops.h:103-136).
+    One host sync to learn the output count (the reference syncs for the same reason, :126-135)."""
+    indices = _cuda(indices, "indices")
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4
+    indices = indices.contiguous()
+    ks, st, pad, dil = _i3(ksize), _i3(stride), _i3(padding), _i3(dilation)
+    oshape = conv_output_shape(spatial_shape, ks, st, pad, dil)
+    if min(oshape) <= 0:
+        raise RuntimeError("wsis_b200: empty output spatial shape %s" % (oshape,))
+    K = ks[0] * ks[1] * ks[2]
+    N = indices.shape[0]
+    dev = indices.device
+    nbr_in = torch.empty((N, K), dtype=torch.int32, device=dev)
+    if N == 0:
+        return Rulebook("conv", K, 0, 0, nbr_in, torch.empty((0, K), dtype=torch.int32, device=dev),
+                        torch.empty((0, 4), dtype=torch.int32, device=dev)), oshape
+    tpi = 1
+    for d in range(3):
+        tpi *= (ks[d] + st[d] - 1) // st[d]
+    slots = lib().value("wsis_hash_slots", N * tpi)
+    keys = torch.empty((slots,), dtype=torch.int64, device=dev)
+    vals = torch.empty((slots,), dtype=torch.int32, device=dev)
+    rank = torch.empty((N * K + 1,), dtype=torch.int32, device=dev)
+    scan_ws = _bytes(lib().value("wsis_scan_ws_bytes", N * K), dev)
+    n_out_dev = torch.empty((1,), dtype=torch.int32, device=dev)
+    lib().call("wsis_rulebook_conv_count", _ptr(indices), N, _c3(ks), _c3(st), _c3(pad), _c3(dil), _c3(oshape),
+               _ptr(keys), _ptr(vals), slots, _ptr(nbr_in), _ptr(rank), _ptr(scan_ws), _ptr(n_out_dev), _stream())
+    n_out = int(n_out_dev.item())
+    out_coords = torch.empty((n_out, 4), dtype=torch.int32, device=dev)
+    nbr_out = torch.empty((n_out, K), dtype=torch.int32, device=dev)
+    slot_rank = torch.empty((slots,), dtype=torch.int32, device=dev)
+    lib().call("wsis_rulebook_conv_fill", _ptr(indices), N, K, _ptr(keys), _ptr(vals), slots, _ptr(nbr_in), _ptr(rank),
+               _ptr(slot_rank), n_out, _ptr(out_coords), _ptr(nbr_out), _stream())
+    return Rulebook("conv", K, N, n_out, nbr_in, nbr_out, out_coords), oshape
+
+
+def rulebook_from_pairs(pairs, num, n_in, n_out, subm):
+    """For callers that bring their own reference-format pairs (ops.indice_conv drop-in, spconv/ops.py:101-116)."""
+    pairs = _cuda(pairs, "indice_pairs").contiguous()
+    num = _cuda(num, "indice_pair_num").contiguous()
+    assert pairs.dtype == torch.int32 and num.dtype == torch.int32
+    K, stride = pairs.shape[0], pairs.shape[2]
+    dev = pairs.device
+    nbr_in = torch.full((n_in, K), -1, dtype=torch.int32, device=dev)
+    lib().call("wsis_nbr_from_pairs", _ptr(pairs), _ptr(num), stride, K, 0, _ptr(nbr_in), _stream())
+    nbr_out = None
+    if not subm:
+        nbr_out = torch.full((n_out, K), -1, dtype=torch.int32, device=dev)
+        lib().call("wsis_nbr_from_pairs", _ptr(pairs), _ptr(num), stride, K, 1, _ptr(nbr_out), _stream())
+    rb = Rulebook("subm" if subm else "conv", K, n_in, n_out, nbr_in, nbr_out, None)
+    rb._pairs = (pairs, num)
+    return rb
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sparse convolution
+# ---------------------------------------------------------------------------------------------------------
+class PackedWeights:
+    """Pre-swizzled bf16 (hi[,mid]) image of a conv weight for the tcgen05 kernel; cached per (weight version)."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, weight3, transpose_w, precision):
+        Cin, Cout = (weight3.shape[2], weight3.shape[1]) if transpose_w else (weight3.shape[1], weight3.shape[2])
+        key = (weight3.data_ptr(), weight3._version, tuple(weight3.shape), transpose_w, precision)
+        if key != self.key:
+            K = weight3.shape[0]
+            nbytes = lib().value("wsis_conv_pack_bytes", K, Cin, Cout, precision)
+            buf = _bytes(nbytes, weight3.device)
+            lib().call("wsis_conv_pack_weights", _ptr(weight3), K, Cin, Cout, int(transpose_w), precision, _ptr(buf),
+                       _stream())
+            self.key, self.buf = key, buf
+        return self.buf
+
+
+def umma_supported(Cin, Cout):
+    return bool(lib().value("wsis_conv_umma_supported", int(Cin), int(Cout)))
+
+
+def sparse_conv(src, weight3, map_, n_dst, flip, transpose_w=False, prologue=None, residual=None, packed=None,
+                precision=None):
+    """dst[r] = residual[r] + sum_k prologue(src[map[r,k']]) @ W[k]  (W[k]^T when transpose_w).
+
+    src f32[n_src, Cin]; weight3 f32[K, Cin_w, Cout_w]; map_ int32[n_dst, K]."""
+    src = _cuda(src, "features")
+    if src.dtype != torch.float32:
+        raise RuntimeError("wsis_b200: features must be float32, got %s" % src.dtype)
+    src = src.contiguous()
+    weight3 = weight3.detach()
+    if weight3.dtype != torch.float32 or not weight3.is_cuda:
+        raise RuntimeError("wsis_b200: filters must be a float32 CUDA tensor, got %s on %s" % (weight3.dtype, weight3.device))
+    if not weight3.is_contiguous():
+        weight3 = weight3.contiguous()
+    K = weight3.shape[0]
+    Cin, Cout = (weight3.shape[2], weight3.shape[1]) if transpose_w else (weight3.shape[1], weight3.shape[2])
+    if src.shape[1] != Cin:
+        raise RuntimeError("wsis_b200: feature width %d != filter in-planes %d" % (src.shape[1], Cin))
+    if map_.shape[0] != n_dst or map_.shape[1] != K:
+        raise RuntimeError("wsis_b200: neighbour map shape %s does not match (n_dst=%d, K=%d)" %
+                           (tuple(map_.shape), n_dst, K))
+    dst = torch.empty((n_dst, Cout), dtype=torch.float32, device=src.device)
+    if n_dst == 0:
+        return dst
+    scale = shift = None
+    relu = 0
+    if prologue is not None:
+        scale, shift, relu = prologue
+        scale, shift = scale.contiguous(), shift.contiguous()
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.shape == dst.shape and residual.dtype == torch.float32
+    precision = precision or _PRECISION
+    if precision != "simt" and umma_supported(Cin, Cout):
+        prec = 3 if precision == "fp32" else 1
+        packed = packed if packed is not None else PackedWeights()
+        buf = packed.get(weight3, bool(transpose_w), prec)
+        lib().call("wsis_conv_umma", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(buf), Cin, Cout, prec,
+                   _ptr(scale), _ptr(shift), int(relu), _ptr(residual), _ptr(dst), _stream())
+    else:
+        lib().call("wsis_conv_simt", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(weight3), int(transpose_w), Cin,
+                   Cout, _ptr(scale), _ptr(shift), int(relu), _ptr(residual), _ptr(dst), _stream())
+    return dst
+
+
+def sparse_conv_wgrad(src, map_, n_dst, flip, grad_out, K, Cin, Cout, prologue=None):
+    """dW[k] = sum_r prologue(src[map[r,k']])^T grad_out[r]   -> f32[K, Cin, Cout]."""
+    src = _cuda(src, "features").contiguous()
+    grad_out = grad_out.contiguous()
+    dW = torch.empty((K, Cin, Cout), dtype=torch.float32, device=src.device)
+    scale = shift = None
+    relu = 0
+    if prologue is not None:
+        scale, shift, relu = prologue
+    lib().call("wsis_conv_wgrad", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(grad_out), Cin, Cout, _ptr(scale),
+               _ptr(shift), int(relu), _ptr(dW), _stream())
+    return dW
+
+
+def affine_relu(x, scale, shift, relu=True, out=None):
+    """Eval-mode BatchNorm1d folded to y = x*scale+shift, optionally ReLU; one pass."""
+    x = _cuda(x, "x").contiguous()
+    out = torch.empty_like(x) if out is None else out
+    scale, shift = scale.contiguous(), shift.contiguous()  # temporaries must outlive the launch call
+    lib().call("wsis_affine_relu", _ptr(x), x.shape[0], x.shape[1], _ptr(scale), _ptr(shift), int(relu), _ptr(out),
+               _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# voxelization (pointgroup_ops contract)
+# ---------------------------------------------------------------------------------------------------------
+def voxelization_idx(coords, batch_size=None, mode=4):
+    """coords int64[N,4] -> (voxel_locs int64[M,4], p2v int32[N], v2p int32[M,1+maxActive]).
+    CPU tensors use the CUDA-free host routine (DataLoader workers, scannetv2_dataset.py:449); CUDA tensors
+    use the device hash-table path.  Both number voxels in first-occurrence order."""
+    assert coords.dtype == torch.int64 and coords.dim() == 2 and coords.shape[1] == 4
+    coords = coords.contiguous()
+    N = coords.shape[0]
+    if not coords.is_cuda:
+        ma = ctypes.c_int32(0)
+        M = lib().value("wsis_voxelize_idx_host", _ptr(coords), N, None, None, None, 0, ctypes.byref(ma))
+        if M < 0:
+            raise RuntimeError("voxelization_idx: " + lib().last_error())
+        locs = torch.empty((M, 4), dtype=torch.int64)
+        p2v = torch.empty((N,), dtype=torch.int32)
+        v2p = torch.empty((M, 1 + ma.value), dtype=torch.int32)
+        M2 = lib().value("wsis_voxelize_idx_host", _ptr(coords), N, _ptr(locs), _ptr(p2v), _ptr(v2p), 1 + ma.value,
+                         ctypes.byref(ma))
+        if M2 != M:
+            raise RuntimeError("voxelization_idx: " + lib().last_error())
+        return locs, p2v, v2p
+    dev = coords.device
+    p2v = torch.empty((N,), dtype=torch.int32, device=dev)
+    counts = torch.empty((3,), dtype=torch.int32, device=dev)
+    ws = _bytes(lib().value("wsis_voxelize_ws_bytes", N), dev)
+    lib().call("wsis_voxelize_idx_count", _ptr(coords), N, _ptr(p2v), _ptr(counts), _ptr(ws), _stream())
+    M, ma, err = (int(x) for x in counts.tolist())
+    if err:
+        raise RuntimeError("voxelization_idx: coordinates must lie in [0, 65535]")
+    locs = torch.empty((M, 4), dtype=torch.int64, device=dev)
+    v2p = torch.empty((M, 1 + ma), dtype=torch.int32, device=dev)
+    lib().call("wsis_voxelize_idx_fill", _ptr(coords), N, _ptr(p2v), M, ma, _ptr(locs), _ptr(v2p), _ptr(ws), _stream())
+    return locs, p2v, v2p
+
+
+def voxelization_fwd(feats, v2p):
+    feats = _cuda(feats, "feats").contiguous()
+    v2p = _cuda(v2p, "v2p_map").contiguous()
+    assert feats.dtype == torch.float32 and v2p.dtype == torch.int32
+    M, C = v2p.shape[0], feats.shape[1]
+    out = torch.empty((M, C), dtype=torch.float32, device=feats.device)
+    lib().call("wsis_voxelize_mean_fwd", _ptr(feats), _ptr(v2p), M, v2p.shape[1], C, _ptr(out), _stream())
+    return out
+
+
+def voxelization_bwd(dout, v2p, n_points):
+    dout = _cuda(dout, "d_output_feats").contiguous()
+    v2p = v2p.contiguous()
+    M, C = dout.shape
+    df = torch.empty((n_points, C), dtype=torch.float32, device=dout.device)
+    lib().call("wsis_voxelize_mean_bwd", _ptr(dout), _ptr(v2p), M, v2p.shape[1], C, n_points, _ptr(df), _stream())
+    return df
+
+
+# ---------------------------------------------------------------------------------------------------------
+# segmented reductions (torch_scatter.scatter contract)
+# ---------------------------------------------------------------------------------------------------------
+class SegmentIndex:
+    """CSR of an unsorted id vector, built once per scene and shared by every reduction over it."""
+
+    def __init__(self, ids, num_segments):
+        ids = _cuda(ids, "index")
+        assert ids.dtype == torch.int64 and ids.dim() == 1
+        ids = ids.contiguous()
+        self.ids = ids
+        self.n, self.S = ids.shape[0], int(num_segments)
+        dev = ids.device
+        self.order = torch.empty((max(self.n, 1),), dtype=torch.int32, device=dev)
+        self.offsets = torch.empty((self.S + 1,), dtype=torch.int32, device=dev)
+        ws = _bytes(lib().value("wsis_segment_csr_ws_bytes", self.n, self.S), dev)
+        lib().call("wsis_segment_csr", _ptr(ids), self.n, self.S, _ptr(self.order), _ptr(self.offsets), _ptr(ws),
+                   _stream())
+
+
+_REDUCE = {"sum": 0, "add": 0, "mean": 1, "max": 2}
+
+
+def segment_reduce(src, seg, reduce="mean", gather=None):
+    """out[s] = reduce over rows i with ids[i]==s of src[gather[i] if gather is given else i]."""
+    src = _cuda(src, "src")
+    squeeze = src.dim() == 1
+    src2 = (src.unsqueeze(1) if squeeze else src).contiguous()
+    assert src2.dtype == torch.float32
+    out = torch.empty((seg.S, src2.shape[1]), dtype=torch.float32, device=src.device)
+    if gather is not None:
+        assert gather.dtype == torch.int32
+        gather = gather.contiguous()
+    lib().call("wsis_segment_reduce", _ptr(src2), _ptr(gather), _ptr(seg.order), _ptr(seg.offsets), seg.S, src2.shape[1],
+               _REDUCE[reduce], _ptr(out), _stream())
+    return out[:, 0] if squeeze else out
+
+
+def scatter(src, index, dim=0, reduce="sum", dim_size=None):
+    """torch_scatter.scatter(src, index, dim=0, reduce=...) drop-in for the calls at backbone_3D_WSIS.py:188,225,
+    232,244.  Like torch_scatter, dim_size=None costs one host sync for index.max()."""
+    assert dim == 0
+    if dim_size is None:
+        dim_size = int(index.max().item()) + 1 if index.numel() > 0 else 0
+    return segment_reduce(src, SegmentIndex(index, dim_size), reduce)
+
+
+def gather_rows(src, idx):
+    src = _cuda(src, "src").contiguous()
+    idx = idx.contiguous()
+    assert idx.dtype == torch.int32 and src.dtype == torch.float32
+    out = torch.empty((idx.shape[0], src.shape[1]), dtype=torch.float32, device=src.device)
+    lib().call("wsis_gather_rows", _ptr(src), _ptr(idx), idx.shape[0], src.shape[1], _ptr(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# affinity + random walk
+# ---------------------------------------------------------------------------------------------------------
+def edge_attention(q, k, v, ecc, centers, edge_u, edge_v, eseg, pos_mlp):
+    """backbone_3D_WSIS.py:209-249 in one kernel.  Returns (edge_affinity f32[E], sp_feat f32[S,64])."""
+    q, k, v, ecc, centers = (_cuda(t, "attention input").contiguous() for t in (q, k, v, ecc, centers))
+    S, D = q.shape
+    E = edge_u.shape[0]
+    aff = torch.empty((E,), dtype=torch.float32, device=q.device)
+    sp = torch.empty((S, D), dtype=torch.float32, device=q.device)
+    edge_u, edge_v, pos_mlp = edge_u.contiguous(), edge_v.contiguous(), pos_mlp.contiguous()
+    assert edge_u.dtype == torch.int64 and edge_v.dtype == torch.int64 and pos_mlp.numel() == 81
+    lib().call("wsis_edge_attention", _ptr(q), _ptr(k), _ptr(v), _ptr(ecc), _ptr(centers), _ptr(edge_u), _ptr(edge_v),
+               _ptr(eseg.order), _ptr(eseg.offsets), S, E, D, _ptr(pos_mlp), _ptr(aff), _ptr(sp), _stream())
+    return aff, sp
+
+
+def pack_pos_mlp(fc_position):
+    """fc_position = Sequential(Linear(3,16), ReLU, Linear(16,1)) (backbone_3D_WSIS.py:110-114) -> f32[81]."""
+    l1, l2 = fc_position[0], fc_position[2]
+    return torch.cat([l1.weight.detach().reshape(-1), l1.bias.detach().reshape(-1), l2.weight.detach().reshape(-1),
+                      l2.bias.detach().reshape(-1)]).float().contiguous()
+
+
+def random_walk(edge_u, edge_v, affinity, seed_label, pred, conf, class_num, iterations, useg=None, vseg=None):
+    """weak_label_propagation (scannetv2_dataset.py:664-735) on the device, float64.
+    Returns (pseudo int32[S] with -100 = none, score float64[S])."""
+    edge_u = _cuda(edge_u, "edge_u").contiguous()
+    edge_v = edge_v.contiguous()
+    S = seed_label.shape[0]
+    E = edge_u.shape[0]
+    dev = edge_u.device
+    useg = useg or SegmentIndex(edge_u, S)
+    vseg = vseg or SegmentIndex(edge_v, S)
+    pseudo = torch.empty((S,), dtype=torch.int32, device=dev)
+    score = torch.empty((S,), dtype=torch.float64, device=dev)
+    ws = _bytes(lib().value("wsis_random_walk_ws_bytes", S, int(class_num)), dev)
+    # converted copies are bound to names so that they outlive the launch call (a temporary freed right after
+    # _ptr() would be handed to the next temporary by the caching allocator)
+    aff32 = affinity.contiguous().float()
+    seed32, pred32, conf32 = seed_label.int().contiguous(), pred.int().contiguous(), conf.float().contiguous()
+    lib().call("wsis_random_walk", _ptr(edge_u), _ptr(edge_v), _ptr(aff32), _ptr(useg.order), _ptr(useg.offsets),
+               _ptr(vseg.order), _ptr(vseg.offsets), S, E, _ptr(seed32), _ptr(pred32), _ptr(conf32), int(class_num),
+               int(iterations), _ptr(pseudo), _ptr(score), _ptr(ws), _stream())
+    return pseudo, score

@@ -1,0 +1,77 @@
+"""Scene-level hot path: the step body of the reference's drivers, from a collated host batch to the network
+outputs and (optionally) the propagated pseudo labels.
+
+    forward:      train_scannetv2.py:149-198 / test_scannetv2.py:140-190
+                  (.cuda() copies -> superpoint centres -> voxelization -> SparseConvTensor -> Network)
+    propagation:  train_scannetv2.py:554-575 -> modules/datasets/scannetv2_dataset.py:664-735
+"""
+from types import SimpleNamespace
+
+import torch
+
+import pointgroup_ops
+import spconv
+
+from . import ops as W
+from .model import GraphInfo, Network
+
+DEFAULT_MODEL_CFG = dict(input_channel=3, use_coords=True, blocks=5, block_reps=2, media=32, classes=20,
+                         fix_module="[]")  # config/ScanNet_v2_3D_WSIS.yaml:37-47
+
+# tensors the forward needs on the device (what train_scannetv2.py:149-172 moves with .cuda())
+_DEVICE_KEYS = ("locs", "locs_float", "feats", "superpoint", "edge_u_list", "edge_v_list", "ecc_edge_index",
+                "ecc_edgefeats", "seed_label")
+
+
+def build_network(cfg=None, seed=123, device="cuda"):
+    """Random-init network of the reference architecture under torch.manual_seed(seed) (config/*.yaml:3)."""
+    cfg = dict(DEFAULT_MODEL_CFG, **(cfg or {}))
+    torch.manual_seed(seed)
+    net = Network(SimpleNamespace(**cfg))
+    return net.to(device)
+
+
+def pin_batch(batch):
+    return {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def to_device(batch, device="cuda", non_blocking=True):
+    """Host -> device copy of one collated batch; returns (device batch, bytes copied)."""
+    out, nbytes = dict(batch), 0
+    for k in _DEVICE_KEYS:
+        if k in batch:
+            out[k] = batch[k].to(device, non_blocking=non_blocking)
+            nbytes += batch[k].numel() * batch[k].element_size()
+    return out, nbytes
+
+
+def forward_batch(model, dbatch, use_coords=True, mode=4):
+    """Voxelization + UNet + pooling + affinity for one device-resident batch.  Returns (ret dict, aux dict)."""
+    locs = dbatch["locs"]
+    S = dbatch["num_superpoints"]
+    voxel_locs, p2v_map, v2p_map = pointgroup_ops.voxelization_idx(locs, dbatch["batch_size"], mode)
+    coords_float = dbatch["locs_float"]
+    superpoint = dbatch["superpoint"]
+    sp_index = W.SegmentIndex(superpoint, S)
+    centers = W.segment_reduce(coords_float, sp_index, "mean")                       # train_scannetv2.py:177
+    feats = torch.cat((dbatch["feats"], coords_float), 1) if use_coords else dbatch["feats"]
+    voxel_feats = pointgroup_ops.voxelization(feats, v2p_map, mode)                 # :189
+    input_ = spconv.SparseConvTensor(voxel_feats, voxel_locs.int(), dbatch["spatial_shape"], dbatch["batch_size"])
+    eindex = W.SegmentIndex(dbatch["edge_u_list"], S)
+    extra = {"superpoint": superpoint, "GIs": [GraphInfo(dbatch["ecc_edge_index"], dbatch["ecc_edgefeats"])],
+             "edge_u_list": dbatch["edge_u_list"], "edge_v_list": dbatch["edge_v_list"],
+             "superpoint_cenetr_xyz": centers, "sp_index": sp_index, "edge_index_u": eindex, "num_superpoints": S}
+    ret = model(input_, p2v_map, extra)
+    aux = {"voxel_locs": voxel_locs, "p2v_map": p2v_map, "v2p_map": v2p_map, "centers": centers, "input": input_,
+           "edge_index_u": eindex}
+    return ret, aux
+
+
+def propagate_labels(ret, dbatch, aux, iterations, class_num=20):
+    """Random-walk pseudo labels for a batch of ONE scene (the reference propagates with batch_size=1,
+    train_scannetv2.py:498).  Returns (pseudo int32[S], score float64[S])."""
+    prob = torch.softmax(ret['sp_semantic_scores'], dim=-1)                          # train_scannetv2.py:555-557
+    conf, pred = prob.max(1)
+    vseg = W.SegmentIndex(dbatch["edge_v_list"], dbatch["num_superpoints"])
+    return W.random_walk(dbatch["edge_u_list"], dbatch["edge_v_list"], ret['edge_affinity'], dbatch["seed_label"],
+                         pred, conf, class_num, iterations, useg=aux["edge_index_u"], vseg=vseg)

@@ -1,0 +1,212 @@
+/*
+ * wsis_b200.h -- C ABI of the B200-native 3D-WSIS scene-level hot path.
+ *
+ * This is the drop-in boundary: what the reference binds through
+ *   - the 12 `torch.ops.spconv.*` operators registered at modules/lib/spconv/src/spconv/all.cc:19-34
+ *     (signatures: include/spconv/spconv_ops.h:27-33, 253-256, 351-355), and
+ *   - the external `pointgroup_ops` extension (call sites modules/datasets/scannetv2_dataset.py:449,
+ *     train_scannetv2.py:189) and `torch_scatter.scatter` (modules/model/backbone_3D_WSIS.py:188,225-244),
+ * is exported here as plain `extern "C"` functions over raw device pointers, sizes and a CUDA stream.
+ * No torch types cross this boundary.  INTEGRATION.md shows the reference-side ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns and allocates all outputs and workspaces (the reference allocates inside the op,
+ *     spconv_ops.h:55-62,284-287); `*_ws_bytes` helpers give workspace sizes;
+ *   - every call is asynchronous on `stream` (no device->host sync inside, unlike spconv_ops.h:264),
+ *     except where the name says `_host`/`_sync`;
+ *   - return value: 0 = ok, non-zero = error; `wsis_last_error()` returns a thread-local message.  The
+ *     Python host raises RuntimeError, matching TV_ASSERT_RT_ERR (include/tensorview/tensorview.h:70-101);
+ *   - coords are int32 [N,4] = (batch, x, y, z) like spconv indices; each coordinate must be in [0, 65535].
+ *   - a "neighbour map" `map[n_dst, K]` (int32, -1 = none) is the output-stationary form of the rulebook:
+ *       conv:   dst[r] = sum_k src[ map[r, flip ? K-1-k : k] ] * W[k]
+ *     For a rulebook with pairs (k, in=i, out=o) (the reference's indicePairs[k,0/1,:]):
+ *       nbr_in [i,k] = o   and   nbr_out[o,k] = i.
+ *     submanifold conv: nbr_out[o,k] == nbr_in[o,K-1-k], so only nbr_in is stored and flip=1 is used.
+ */
+#ifndef WSIS_B200_H_
+#define WSIS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *wsis_stream_t; /* cudaStream_t */
+
+/* ---------------------------------------------------------------------------------------------- */
+/* library                                                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+int wsis_version(void);
+const char *wsis_last_error(void);
+/* sm_count / compute capability of the current device; fails when no CUDA device is usable. */
+int wsis_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t wsis_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* primitives: fill, exclusive scan, stable LSD radix sort (hand-written; replace torch::_unique's  */
+/* thrust sort at spconv_ops.h:126 and torch_scatter's atomics)                                   */
+/* ---------------------------------------------------------------------------------------------- */
+int wsis_fill_i32(int32_t *dst, int64_t n, int32_t value, wsis_stream_t stream);
+int64_t wsis_scan_ws_bytes(int64_t n);
+/* out[0..n] (n+1 entries): out[i] = sum_{j<i} in[j]; out[n] = total.  in may alias out[0..n-1]. */
+int wsis_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, void *ws, wsis_stream_t stream);
+int64_t wsis_sort_ws_bytes(int64_t n);
+/* stable sort of (key,val) by key bits [begin_bit,end_bit); result is written to keys_out/vals_out. */
+int wsis_sort_pairs_u32(const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out,
+                        int64_t n, int begin_bit, int end_bit, void *ws, wsis_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* rulebook (indice pairs): GPU hash table instead of the reference's dense batch*D*H*W grid        */
+/* (spconv_ops.h:60-62; indice.cu.h:150-208 subm, :22-65,112-148 strided)                          */
+/* ---------------------------------------------------------------------------------------------- */
+/* power-of-two slot count for n keys (load factor <= 0.5) */
+int64_t wsis_hash_slots(int64_t n);
+
+/* Submanifold rulebook (replaces getIndicePair<3> subm branch, spconv_ops.h:86-102).
+ * hash_keys uint64[slots], hash_vals int32[slots]: workspaces, (re)initialised by the call.
+ * nbr_in int32[N,K] out.  Duplicate coords: the largest row index wins (CPU reference, geometry.h:272-277). */
+int wsis_rulebook_subm(const int32_t *coords, int64_t N, const int32_t ksize[3], const int32_t dilation[3],
+                       const int32_t spatial_shape[3], uint64_t *hash_keys, int32_t *hash_vals, int64_t slots,
+                       int32_t *nbr_in, wsis_stream_t stream);
+
+/* Strided ("regular") sparse conv rulebook (replaces getIndicePair<3> conv branch, spconv_ops.h:103-136).
+ * Phase 1 (count): builds the output hash set, numbers the outputs in the CPU reference's first-touch order
+ *   (geometry.h:181-187) and writes the output count to n_out_dev[0].
+ *   nbr_in int32[N,K] receives hash slot ids (scratch form);  rank_ws int32[N*K+1]; slot_rank int32[slots].
+ * Phase 2 (fill), after the host has read n_out and allocated: out_coords int32[n_out,4], nbr_out int32[n_out,K]
+ *   (pre-filled with -1 by the call), nbr_in rewritten to output row ids. */
+int wsis_rulebook_conv_count(const int32_t *coords, int64_t N, const int32_t ksize[3], const int32_t stride[3],
+                             const int32_t padding[3], const int32_t dilation[3], const int32_t out_shape[3],
+                             uint64_t *hash_keys, int32_t *hash_vals, int64_t slots, int32_t *nbr_in,
+                             int32_t *rank_ws, void *scan_ws, int32_t *n_out_dev, wsis_stream_t stream);
+int wsis_rulebook_conv_fill(const int32_t *coords, int64_t N, int K, const uint64_t *hash_keys,
+                            const int32_t *hash_vals, int64_t slots, int32_t *nbr_in, const int32_t *rank_ws,
+                            int32_t *slot_rank, int64_t n_out, int32_t *out_coords, int32_t *nbr_out,
+                            wsis_stream_t stream);
+
+/* Reference-format rulebook from nbr_in: pairs int32[K,2,N] (-1 padded) and num int32[K], in exactly the
+ * CPU reference's order (ascending input row inside each offset; geometry.h:176-190,281-289), which is a
+ * valid instance of the GPU reference's atomics-ordered output (indice.cu.h:57,202).
+ * pos_ws int32[K*N+1]; scan_ws from wsis_scan_ws_bytes(K*N). */
+int wsis_pairs_from_nbr(const int32_t *nbr_in, int64_t N, int K, int32_t *pairs, int32_t *num, int32_t *pos_ws,
+                        void *scan_ws, wsis_stream_t stream);
+/* Inverse direction, for callers that hand us reference-format pairs (ops.indice_conv drop-in):
+ * map int32[n_dst,K] must be pre-filled with -1; dst_side = 1 builds nbr_out (keyed by pairs[k,1,:]),
+ * dst_side = 0 builds nbr_in (keyed by pairs[k,0,:]). */
+int wsis_nbr_from_pairs(const int32_t *pairs, const int32_t *num, int64_t pair_stride, int K, int dst_side,
+                        int32_t *map, wsis_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* sparse convolution = gather -> per-offset contraction -> (no scatter: output-stationary)          */
+/* replaces indiceConv<T> / indiceConvBackward<T>, spconv_ops.h:253-349, 351-433                    */
+/* ---------------------------------------------------------------------------------------------- */
+/* Optional fused prologue on the gathered rows: x' = relu?(x * in_scale[c] + in_shift[c]) (eval-mode
+ * BatchNorm1d + ReLU that precede every conv in ResidualBlock/UBlock, sparse_unet3d.py:163-172,258-298);
+ * missing neighbours stay exactly zero.  Optional fused epilogue: dst += residual (identity branch).
+ * Pass NULL to disable either.  W is the reference layout [K, Cin_w, Cout_w] (conv.py:98-99);
+ * transpose_w = 1 contracts with W[k]^T (dgrad), i.e. Cin = Cout_w and Cout = Cin_w. */
+
+/* exact-fp32 SIMT path (any Cin/Cout; used for the 6->32 input conv, odd widths and as the GPU-side
+ * cross-check of the tensor-core path) */
+int wsis_conv_simt(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const float *W,
+                   int transpose_w, int Cin, int Cout, const float *in_scale, const float *in_shift, int in_relu,
+                   const float *residual, float *dst, wsis_stream_t stream);
+
+/* tcgen05 tensor-core path.  precision: 1 = bf16 operands (1e-2 contract), 3 = bf16x3 split operands with
+ * fp32 accumulation in TMEM (1e-4 contract).  Requires Cin % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 256. */
+int wsis_conv_umma_supported(int Cin, int Cout);
+int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision);
+int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
+                           wsis_stream_t stream);
+int wsis_conv_umma(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const void *packed,
+                   int Cin, int Cout, int precision, const float *in_scale, const float *in_shift, int in_relu,
+                   const float *residual, float *dst, wsis_stream_t stream);
+
+/* dW[k] = sum_r prologue(src[map[r,k']])^T . g[r]   (fp32, dW is zeroed by the call). */
+int wsis_conv_wgrad(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const float *g, int Cin,
+                    int Cout, const float *in_scale, const float *in_shift, int in_relu, float *dW,
+                    wsis_stream_t stream);
+
+/* fused eval-BatchNorm(+ReLU) on a feature matrix, in place allowed: y = relu?(x*scale[c]+shift[c]) */
+int wsis_affine_relu(const float *x, int64_t n, int C, const float *scale, const float *shift, int relu, float *y,
+                     wsis_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* voxelization (pointgroup_ops; third-party, source not in the reference tree)                     */
+/* ---------------------------------------------------------------------------------------------- */
+/* Host (CUDA-free, fork-safe) voxelization_idx for DataLoader workers (scannetv2_dataset.py:449).
+ * Two-phase: call with voxel_locs_host == NULL to get M (return value, <0 on error) and *max_active;
+ * then with buffers voxel_locs int64[M,4], p2v int32[N], v2p int32[M,1+max_active] (zero-filled by the call). */
+int64_t wsis_voxelize_idx_host(const int64_t *coords_host, int64_t N, int64_t *voxel_locs_host, int32_t *p2v_host,
+                               int32_t *v2p_host, int32_t v2p_stride, int32_t *max_active_host);
+
+/* Device voxelization_idx (same numbering: first-occurrence order; v2p lists in ascending point order).
+ * Phase 1: p2v int32[N] out; counts_dev int32[3]: [0] = M, [1] = max_active, [2] = 1 if a coordinate was
+ *   outside [0,65535] (result invalid).
+ *   ws: wsis_voxelize_ws_bytes(N).  Phase 2 (after the host read M, max_active): voxel_locs int64[M,4],
+ *   v2p int32[M, 1+max_active] (zero-filled by the call). */
+int64_t wsis_voxelize_ws_bytes(int64_t N);
+int wsis_voxelize_idx_count(const int64_t *coords, int64_t N, int32_t *p2v, int32_t *counts_dev, void *ws,
+                            wsis_stream_t stream);
+int wsis_voxelize_idx_fill(const int64_t *coords, int64_t N, const int32_t *p2v, int64_t M, int32_t max_active,
+                           int64_t *voxel_locs, int32_t *v2p, void *ws, wsis_stream_t stream);
+
+/* voxelization(feats, v2p, mode=4 mean) forward / backward (train_scannetv2.py:189). */
+int wsis_voxelize_mean_fwd(const float *feats, const int32_t *v2p, int64_t M, int32_t v2p_stride, int C, float *out,
+                           wsis_stream_t stream);
+int wsis_voxelize_mean_bwd(const float *dout, const int32_t *v2p, int64_t M, int32_t v2p_stride, int C, int64_t N,
+                           float *dfeats, wsis_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* segmented reductions (torch_scatter.scatter(dim=0) at backbone_3D_WSIS.py:188,225,232,244)        */
+/* ---------------------------------------------------------------------------------------------- */
+/* CSR of an unsorted segment-id vector: order int32[N] = rows sorted stably by id, offsets int32[S+1]. */
+int64_t wsis_segment_csr_ws_bytes(int64_t N, int64_t S);
+int wsis_segment_csr(const int64_t *ids, int64_t N, int64_t S, int32_t *order, int32_t *offsets, void *ws,
+                     wsis_stream_t stream);
+/* out[s,:] = reduce_{j in seg s} src[ gather ? gather[order[j]] : order[j], :]; one warp per segment, fixed
+ * summation order, no atomics.  reduce: 0 = sum, 1 = mean (sum / max(count,1)), 2 = max (empty -> 0).
+ * `gather` (int32[N] or NULL) fuses the voxel->point gather output.features[p2v] (backbone_3D_WSIS.py:179)
+ * with the superpoint pooling (:188). */
+int wsis_segment_reduce(const float *src, const int32_t *gather, const int32_t *order, const int32_t *offsets,
+                        int64_t S, int C, int reduce, float *out, wsis_stream_t stream);
+/* dst[i,:] = src[idx[i],:]  (voxel->point gather, backbone_3D_WSIS.py:179) */
+int wsis_gather_rows(const float *src, const int32_t *idx, int64_t n, int C, float *dst, wsis_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* inter-superpoint affinity (edge attention) and random-walk label propagation                     */
+/* ---------------------------------------------------------------------------------------------- */
+/* backbone_3D_WSIS.py:209-249 fused: position MLP, scaled dot product, segment softmax over edge_u,
+ * weighted aggregation of v and the residual add.  Edges are given as a CSR over u:
+ * eorder int32[E] (edge ids sorted by u), eoffsets int32[S+1] (from wsis_segment_csr on edge_u).
+ * pos_mlp: float[16*3 + 16 + 16 + 1] = fc_position {w1[16,3], b1[16], w2[16], b2}.  D must be 64.
+ * affinity float[E] (original edge order) and sp_feat float[S,D] = ecc + sum_e a_e v_v are written. */
+int wsis_edge_attention(const float *q, const float *k, const float *v, const float *ecc, const float *centers,
+                        const int64_t *edge_u, const int64_t *edge_v, const int32_t *eorder,
+                        const int32_t *eoffsets, int64_t S, int64_t E, int D, const float *pos_mlp,
+                        float *affinity, float *sp_feat, wsis_stream_t stream);
+
+/* Random-walk label propagation (modules/datasets/scannetv2_dataset.py:664-735 + the dense fill at
+ * train_scannetv2.py:565-570), float64 like the reference, exploiting that the transition matrix is
+ * adjacency-masked and that only seed rows of T^(it+1) are read (:714-715).
+ *   edges (u,v) int64[E] with affinity float[E]; adjacency = the same edge set (+ identity);
+ *   seed_label int32[S] (-100 = unlabeled, else class id = vs['semantic_label']);
+ *   pred int32[S], conf float[S]: argmax / max of softmax(sp_semantic_scores).
+ *   (eorder,eoffsets) = CSR of the edges over edge_u, (torder,toffsets) = CSR over edge_v (wsis_segment_csr).
+ *   The edge list must be simple (no duplicate (u,v), no self loops), as produced by the reference's
+ *   preprocessing (data/ScanNetV2/prepare_data_inst_ScanNetV2.py:191-231).
+ * Outputs: pseudo int32[S] (-100 or the seed superpoint id), score double[S].
+ * ws: wsis_random_walk_ws_bytes(S, class_num). */
+int64_t wsis_random_walk_ws_bytes(int64_t S, int class_num);
+int wsis_random_walk(const int64_t *edge_u, const int64_t *edge_v, const float *affinity, const int32_t *eorder,
+                     const int32_t *eoffsets, const int32_t *torder, const int32_t *toffsets, int64_t S, int64_t E,
+                     const int32_t *seed_label, const int32_t *pred, const float *conf, int class_num, int iterations,
+                     int32_t *pseudo, double *score, void *ws, wsis_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSIS_B200_H_ */

@@ -1,0 +1,507 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (include/wsis_b200.h via wsis_b200.ops /
+the drop-in spconv + pointgroup_ops packages), against the CPU oracle on the same seeded inputs, against the
+committed golden fixtures (outputs of the reference itself), and -- at BASELINE.json's full size -- through
+size-independent properties.
+
+Bars: integer / index outputs bit-exact; fp32 path 1e-4 relative; bf16 tensor-core path 1e-2 relative
+(BASELINE.json north_star).  Relative error is max|a-b| / max|b| over a tensor.
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 1e-2
+
+
+def _need_gpu():
+    assert torch.cuda.is_available(), "these tests must run on a CUDA box (-m gpu)"
+
+
+@pytest.fixture(scope="module")
+def W():
+    _need_gpu()
+    from wsis_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def gen_coords(rng, shape, npts, bs):
+    cells = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), -1).reshape(-1, 3)
+    out = []
+    for b in range(bs):
+        sel = rng.permutation(len(cells))[:npts]
+        out.append(np.concatenate([np.full((len(sel), 1), b), cells[sel]], 1))
+    return np.concatenate(out).astype(np.int32)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# primitives
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 255, 2048, 2049, 100003, 1 << 21])
+def test_exclusive_scan(W, n):
+    import ctypes
+    from wsis_b200._lib import lib
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 5, n).astype(np.int32)
+    d = cu(x) if n else torch.empty(0, dtype=torch.int32, device="cuda")
+    out = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib().value("wsis_scan_ws_bytes", n), dtype=torch.uint8, device="cuda")
+    lib().call("wsis_exclusive_scan_i32", W._ptr(d), W._ptr(out), n, W._ptr(ws), W._stream())
+    ref = np.concatenate([[0], np.cumsum(x, dtype=np.int64)]).astype(np.int32)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (1000, 5), (2048, 8), (70001, 12), (300000, 17), (50000, 32)])
+def test_radix_sort_stable(W, n, bits):
+    from wsis_b200._lib import lib
+    rng = np.random.default_rng(n + bits)
+    keys = rng.integers(0, 1 << min(bits, 31), n).astype(np.uint32)
+    if bits == 32:
+        keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    vals = np.arange(n, dtype=np.uint32)
+    dk, dv = cu(keys.view(np.int32)), cu(vals.view(np.int32))
+    ok, ov = torch.empty_like(dk), torch.empty_like(dv)
+    ws = torch.empty(lib().value("wsis_sort_ws_bytes", n), dtype=torch.uint8, device="cuda")
+    lib().call("wsis_sort_pairs_u32", W._ptr(dk), W._ptr(dv), W._ptr(ok), W._ptr(ov), n, 0, bits, W._ptr(ws), W._stream())
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ok.cpu().numpy().view(np.uint32), keys[order])
+    assert np.array_equal(ov.cpu().numpy().view(np.uint32), vals[order])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# rulebooks: bit-exact against the oracle (= the reference CPU path, tests/test_oracle_cpu.py pins that)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bs,ksize,dil", [(1, 3, 1), (2, 3, 1), (2, 3, 2), (1, (1, 3, 3), 1), (2, (3, 1, 3), 1)])
+def test_rulebook_subm_bit_exact(W, orc, bs, ksize, dil):
+    rng = np.random.default_rng(11)
+    shape = [19, 18, 17]
+    c = gen_coords(rng, shape, 1500, bs)
+    pairs, num = orc.rulebook_subm(c, bs, shape, ksize, dil)
+    rb = W.rulebook_subm(cu(c), shape, ksize, dil)
+    gp, gn = rb.pairs()
+    assert np.array_equal(gn.cpu().numpy(), num)
+    assert np.array_equal(gp.cpu().numpy(), pairs)  # same order as the CPU reference, not only the same set
+
+
+@pytest.mark.parametrize("bs,k,s,p,d", [t for t in itertools.product([1, 2], [2, 3], [1, 2, 3], [0, 1, 2], [1, 2])
+                                         if not (t[2] > 1 and t[4] > 1)])
+def test_rulebook_conv_bit_exact(W, orc, bs, k, s, p, d):
+    """The parameter grid of the reference's own testSpConv3d (test/test_conv.py:325-343)."""
+    rng = np.random.default_rng(484)
+    shape = [19, 18, 17]
+    c = gen_coords(rng, shape, 1000, bs)
+    oc, pairs, num, oshape = orc.rulebook_conv(c, bs, shape, k, s, p, d)
+    if min(oshape) <= 0:
+        pytest.skip("empty output shape")
+    rb, gshape = W.rulebook_conv(cu(c), shape, k, s, p, d)
+    assert gshape == oshape
+    gp, gn = rb.pairs()
+    assert np.array_equal(rb.out_coords.cpu().numpy(), oc)
+    assert np.array_equal(gn.cpu().numpy(), num)
+    assert np.array_equal(gp.cpu().numpy(), pairs)
+    # nbr_out is the transpose of nbr_in
+    nin, nout = rb.nbr_in.cpu().numpy(), rb.nbr_out.cpu().numpy()
+    ii, kk = np.nonzero(nin >= 0)
+    assert np.array_equal(nout[nin[ii, kk], kk], ii)
+    assert (nout >= 0).sum() == (nin >= 0).sum()
+
+
+def test_rulebook_edge_cases(W, orc):
+    shape = [8, 8, 8]
+    empty = torch.empty((0, 4), dtype=torch.int32, device="cuda")
+    rb = W.rulebook_subm(empty, shape, 3, 1)
+    p, n = rb.pairs()
+    assert p.shape == (27, 2, 0) and int(n.sum()) == 0
+    rb, _ = W.rulebook_conv(empty, shape, 2, 2, 0, 1)
+    assert rb.n_out == 0
+    # a single voxel in a corner, and a full dense block (every neighbour present)
+    one = np.array([[0, 0, 0, 0]], np.int32)
+    pairs, num = orc.rulebook_subm(one, 1, shape, 3, 1)
+    gp, gn = W.rulebook_subm(cu(one), shape, 3, 1).pairs()
+    assert np.array_equal(gn.cpu().numpy(), num) and np.array_equal(gp.cpu().numpy(), pairs)
+    dense = gen_coords(np.random.default_rng(0), [6, 6, 6], 216, 2)
+    pairs, num = orc.rulebook_subm(dense, 2, [6, 6, 6], 3, 1)
+    gp, gn = W.rulebook_subm(cu(dense), [6, 6, 6], 3, 1).pairs()
+    assert np.array_equal(gn.cpu().numpy(), num) and np.array_equal(gp.cpu().numpy(), pairs)
+    # odd extent: the last row/column is dropped by a k2 s2 conv (9300 -> 9200 pairs)
+    odd = gen_coords(np.random.default_rng(1), [9, 7, 5], 200, 1)
+    oc, pairs, num, osh = orc.rulebook_conv(odd, 1, [9, 7, 5], 2, 2, 0, 1)
+    rb, gs = W.rulebook_conv(cu(odd), [9, 7, 5], 2, 2, 0, 1)
+    gp, gn = rb.pairs()
+    assert gs == osh and np.array_equal(rb.out_coords.cpu().numpy(), oc) and np.array_equal(gp.cpu().numpy(), pairs)
+    assert int(gn.sum()) < 200
+
+
+def test_rulebook_full_size_properties(W):
+    """150 000-voxel shell: pair counts are known from the reference run (1 347 750 pairs,
+    k2s2: 150 000 pairs), the subm rulebook is symmetric and every pair is a true neighbour."""
+    from wsis_b200.synthetic import make_shell
+    c, shape = make_shell()
+    d = cu(c.astype(np.int32))
+    rb = W.rulebook_subm(d, shape, 3, 1)
+    gp, gn = rb.pairs()
+    num = gn.cpu().numpy()
+    assert num.sum() == 1347750 and num[13] == 150000
+    assert np.array_equal(num, num[::-1])
+    pairs = gp.cpu().numpy()
+    for k in (0, 5, 13, 26):
+        i, o = pairs[k, 0, :num[k]], pairs[k, 1, :num[k]]
+        off = np.array([k // 9 - 1, (k // 3) % 3 - 1, k % 3 - 1])
+        assert np.array_equal(c[i, 1:] - c[o, 1:], np.broadcast_to(off, (num[k], 3)))  # in = out + (k - 1)
+        assert np.all(np.diff(i) > 0)  # ascending input rows (CPU reference order)
+    rb2, oshape = W.rulebook_conv(d, shape, 2, 2, 0, 1)
+    assert oshape == [200, 150, 64] and rb2.n_out == 37400
+    assert int(rb2.pairs()[1].sum()) == 150000
+    oc = rb2.out_coords.cpu().numpy()
+    nin = rb2.nbr_in.cpu().numpy()
+    ii, kk = np.nonzero(nin >= 0)
+    assert np.array_equal(oc[nin[ii, kk], 1:], c[ii, 1:] // 2)
+    assert np.unique(oc, axis=0).shape[0] == oc.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sparse convolution
+# ---------------------------------------------------------------------------------------------------------
+def _conv_case(rng, npts, bs, cin, cout, shape=(19, 18, 17)):
+    c = gen_coords(rng, list(shape), npts, bs)
+    f = rng.uniform(-1, 1, (len(c), cin)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (3, 3, 3, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    return c, f, w
+
+
+@pytest.mark.parametrize("cin,cout", [(6, 32), (3, 5), (32, 32), (64, 32), (32, 64), (96, 96), (128, 160), (160, 160),
+                                      (320, 160), (64, 48), (40, 24)])
+@pytest.mark.parametrize("prec,tol", [("simt", 1e-5), ("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_subm_conv_forward(W, orc, cin, cout, prec, tol):
+    rng = np.random.default_rng(cin * 1000 + cout)
+    c, f, w = _conv_case(rng, 1500, 2, cin, cout)
+    pairs, num = orc.rulebook_subm(c, 2, [19, 18, 17], 3, 1)
+    ref = orc.indice_conv(f, w, pairs, num, len(c))
+    rb = W.rulebook_subm(cu(c), [19, 18, 17], 3, 1)
+    out = W.sparse_conv(cu(f), cu(w.reshape(27, cin, cout)), rb.nbr_in, len(c), 1, precision=prec)
+    assert rel(out.cpu().numpy(), ref) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("simt", 2e-6), ("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_conv_fused_prologue_and_residual(W, orc, prec, tol):
+    rng = np.random.default_rng(5)
+    c, f, w = _conv_case(rng, 2000, 1, 64, 32)
+    scale = rng.uniform(0.5, 1.5, 64).astype(np.float32)
+    shift = rng.uniform(-0.3, 0.3, 64).astype(np.float32)
+    res = rng.uniform(-1, 1, (len(c), 32)).astype(np.float32)
+    pairs, num = orc.rulebook_subm(c, 1, [19, 18, 17], 3, 1)
+    ref = orc.indice_conv(np.maximum(f * scale + shift, 0), w, pairs, num, len(c)) + res
+    rb = W.rulebook_subm(cu(c), [19, 18, 17], 3, 1)
+    out = W.sparse_conv(cu(f), cu(w.reshape(27, 64, 32)), rb.nbr_in, len(c), 1, prologue=(cu(scale), cu(shift), 1),
+                        residual=cu(res), precision=prec)
+    assert rel(out.cpu().numpy(), ref) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("simt", 2e-6), ("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_strided_and_inverse_conv(W, orc, prec, tol):
+    """The k2 s2 conv <-> inverse couple of the UNet (sparse_unet3d.py:258-298; reference test_conv.py:443-497)."""
+    rng = np.random.default_rng(6)
+    shape = [20, 18, 16]
+    c = gen_coords(rng, shape, 2500, 2)
+    f = rng.uniform(-1, 1, (len(c), 32)).astype(np.float32)
+    wd = rng.uniform(-1, 1, (8, 32, 64)).astype(np.float32) / 6
+    wu = rng.uniform(-1, 1, (8, 64, 32)).astype(np.float32) / 8
+    oc, pairs, num, _ = orc.rulebook_conv(c, 2, shape, 2, 2, 0, 1)
+    down_ref = orc.indice_conv(f, wd, pairs, num, len(oc))
+    up_ref = orc.indice_conv(down_ref, wu, pairs, num, len(c), inverse=True)
+    rb, _ = W.rulebook_conv(cu(c), shape, 2, 2, 0, 1)
+    down = W.sparse_conv(cu(f), cu(wd), rb.nbr_out, rb.n_out, 0, precision=prec)
+    assert rel(down.cpu().numpy(), down_ref) < tol
+    up = W.sparse_conv(cu(down_ref), cu(wu), rb.nbr_in, rb.n_in, 0, precision=prec)
+    assert rel(up.cpu().numpy(), up_ref) < tol
+
+
+@pytest.mark.parametrize("k,s,p,d", [(3, 1, 1, 1), (3, 2, 1, 1), (2, 2, 0, 1), (3, 1, 2, 2), (3, 3, 0, 1)])
+def test_sparse_conv_vs_dense_conv3d(W, k, s, p, d):
+    """The reference's own golden check (test_conv.py:325-382): SparseConv3d == nn.Conv3d on the densified input,
+    including input and weight gradients, atol 1e-4."""
+    import spconv
+    rng = np.random.default_rng(484)
+    shape, bs, IC, OC = [19, 18, 17], 2, 32, 48
+    c = gen_coords(rng, shape, 1000, bs)
+    f = rng.uniform(-1, 1, (len(c), IC)).astype(np.float32)
+    w = rng.uniform(0, 1, (k, k, k, IC, OC)).astype(np.float32)
+    feats = cu(f).requires_grad_(True)
+    net = spconv.SparseConv3d(IC, OC, k, s, p, d, bias=False).cuda()
+    net.weight.data[:] = cu(w)
+    out = net(spconv.SparseConvTensor(feats, cu(c), shape, bs)).dense()
+    dense = torch.zeros((bs, IC, *shape), device="cuda")
+    dense[cu(c[:, 0]).long(), :, cu(c[:, 1]).long(), cu(c[:, 2]).long(), cu(c[:, 3]).long()] = cu(f)
+    dense.requires_grad_(True)
+    ref_net = torch.nn.Conv3d(IC, OC, k, s, p, d, bias=False).cuda()
+    ref_net.weight.data[:] = cu(w).permute(4, 3, 0, 1, 2).contiguous()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        out_ref = ref_net(dense)
+        dout = cu(rng.uniform(-0.2, 0.2, tuple(out_ref.shape)).astype(np.float32))
+        out.backward(dout)
+        out_ref.backward(dout)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    scale = float(out_ref.abs().max())
+    assert float((out - out_ref).abs().max()) < 1e-4 * max(scale, 1.0)
+    din_ref = dense.grad.permute(0, 2, 3, 4, 1)[cu(c[:, 0]).long(), cu(c[:, 1]).long(), cu(c[:, 2]).long(),
+                                                 cu(c[:, 3]).long()]
+    assert float((feats.grad - din_ref).abs().max()) < 1e-4 * max(float(din_ref.abs().max()), 1.0)
+    dw_ref = ref_net.weight.grad.permute(2, 3, 4, 1, 0)
+    assert float((net.weight.grad - dw_ref).abs().max()) < 1e-4 * max(float(dw_ref.abs().max()), 1.0)
+
+
+@pytest.mark.parametrize("kind", ["subm", "conv", "inverse"])
+def test_conv_backward_vs_oracle(W, orc, kind):
+    """indice_conv_backward (spconv_ops.h:351-433): din and dW."""
+    from spconv import ops as sops
+    rng = np.random.default_rng(8)
+    shape = [20, 18, 16]
+    c = gen_coords(rng, shape, 2000, 2)
+    if kind == "subm":
+        pairs, num = orc.rulebook_subm(c, 2, shape, 3, 1)
+        n_in = n_out = len(c)
+        K, cin, cout = 27, 32, 64
+        outids, gp, gn = sops.get_indice_pairs(cu(c), 2, shape, 3, 1, 1, 1, 0, True)
+    else:
+        oc, pairs, num, _ = orc.rulebook_conv(c, 2, shape, 2, 2, 0, 1)
+        K = 8
+        outids, gp, gn = sops.get_indice_pairs(cu(c), 2, shape, 2, 2, 0, 1, 0, False)
+        if kind == "conv":
+            n_in, n_out, cin, cout = len(c), len(oc), 32, 64
+        else:
+            n_in, n_out, cin, cout = len(oc), len(c), 64, 32
+    f = rng.uniform(-1, 1, (n_in, cin)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (K, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    g = rng.uniform(-1, 1, (n_out, cout)).astype(np.float32)
+    inv = kind == "inverse"
+    din_ref, dw_ref = orc.indice_conv_backward(f, w, g, pairs, num, inverse=inv)
+    din, dw = sops.indice_conv_backward(cu(f), cu(w), cu(g), gp, gn, inv, kind == "subm")
+    assert rel(din.cpu().numpy(), din_ref) < FP32_TOL
+    assert rel(dw.cpu().numpy(), dw_ref) < FP32_TOL
+    # also through foreign reference-format pairs (no neighbour maps attached)
+    gp2 = gp.clone()
+    out = sops.indice_conv(cu(f), cu(w), gp2, gn, n_out, inv, kind == "subm")
+    assert rel(out.cpu().numpy(), orc.indice_conv(f, w, pairs, num, n_out, inverse=inv)) < FP32_TOL
+
+
+def test_conv_full_size_linearity(W):
+    """150k-voxel shell, C=32: conv(a*x + y) == a*conv(x) + conv(y) and the tensor-core path agrees with the
+    exact-fp32 SIMT path (size-independent properties at BASELINE.json's full size)."""
+    from wsis_b200.synthetic import make_shell
+    c, shape = make_shell()
+    rb = W.rulebook_subm(cu(c.astype(np.int32)), shape, 3, 1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.rand((len(c), 32), device="cuda", generator=g) - 0.5
+    y = torch.rand((len(c), 32), device="cuda", generator=g) - 0.5
+    w = (torch.rand((27, 32, 32), device="cuda", generator=g) - 0.5) * 0.3
+    fx = W.sparse_conv(x, w, rb.nbr_in, len(c), 1, precision="fp32")
+    fy = W.sparse_conv(y, w, rb.nbr_in, len(c), 1, precision="fp32")
+    fxy = W.sparse_conv(2.5 * x + y, w, rb.nbr_in, len(c), 1, precision="fp32")
+    s = float(fxy.abs().max())
+    assert float((fxy - (2.5 * fx + fy)).abs().max()) < 2e-4 * s
+    exact = W.sparse_conv(x, w, rb.nbr_in, len(c), 1, precision="simt")
+    assert float((fx - exact).abs().max()) < FP32_TOL * float(exact.abs().max())
+    b16 = W.sparse_conv(x, w, rb.nbr_in, len(c), 1, precision="bf16")
+    assert float((b16 - exact).abs().max()) < BF16_TOL * float(exact.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# voxelization, segmented reductions
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,span", [(1, 4), (5000, 20), (60000, 64), (3000, 3)])
+def test_voxelization_device_matches_oracle(W, orc, n, span):
+    import pointgroup_ops
+    rng = np.random.default_rng(n)
+    coords = np.concatenate([rng.integers(0, 3, (n, 1)), rng.integers(0, span, (n, 3))], 1).astype(np.int64)
+    locs, p2v, v2p = orc.voxelization_idx(coords, 3, 4)
+    glocs, gp2v, gv2p = pointgroup_ops.voxelization_idx(cu(coords), 3, 4)
+    assert np.array_equal(glocs.cpu().numpy(), locs)
+    assert np.array_equal(gp2v.cpu().numpy(), p2v)
+    assert np.array_equal(gv2p.cpu().numpy(), v2p)
+    hlocs, hp2v, hv2p = pointgroup_ops.voxelization_idx(torch.from_numpy(coords), 3, 4)  # host path, same tensors
+    assert np.array_equal(hlocs.numpy(), locs) and np.array_equal(hp2v.numpy(), p2v) and np.array_equal(hv2p.numpy(), v2p)
+    feats = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+    f = cu(feats).requires_grad_(True)
+    out = pointgroup_ops.voxelization(f, gv2p, 4)
+    assert rel(out.detach().cpu().numpy(), orc.voxelization(feats, v2p)) < 1e-6
+    g = rng.uniform(-1, 1, out.shape).astype(np.float32)
+    out.backward(cu(g))
+    assert rel(f.grad.cpu().numpy(), orc.voxelization_backward(g, v2p, n)) < 1e-6
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean", "max"])
+@pytest.mark.parametrize("n,S,C", [(1000, 37, 32), (150000, 3000, 32), (5000, 400, 3), (4000, 100, 1), (300, 299, 64)])
+def test_segment_reduce_matches_oracle(W, orc, reduce, n, S, C):
+    rng = np.random.default_rng(n + S)
+    ids = rng.integers(0, S, n).astype(np.int64)
+    ids[:min(n, S)] = np.arange(min(n, S))  # contiguous ids 0..S-1 as asserted at scannetv2_dataset.py:424
+    src = rng.uniform(-1, 1, (n, C)).astype(np.float32)
+    ref = orc.scatter(src, ids, reduce, S)
+    out = W.scatter(cu(src), cu(ids), 0, reduce, S)
+    assert rel(out.cpu().numpy(), ref) < 2e-6
+    out2 = W.scatter(cu(src), cu(ids), 0, reduce)  # dim_size inferred like torch_scatter
+    assert out2.shape[0] == ids.max() + 1
+
+
+def test_gather_then_pool_fused(W, orc):
+    rng = np.random.default_rng(2)
+    vox = rng.uniform(-1, 1, (5000, 32)).astype(np.float32)
+    p2v = rng.integers(0, 5000, 8000).astype(np.int32)
+    sp = rng.integers(0, 300, 8000).astype(np.int64)
+    ref = orc.scatter(vox[p2v], sp, "mean", 300)
+    seg = W.SegmentIndex(cu(sp), 300)
+    out = W.segment_reduce(cu(vox), seg, "mean", gather=cu(p2v))
+    assert rel(out.cpu().numpy(), ref) < 2e-6
+    assert np.array_equal(W.gather_rows(cu(vox), cu(p2v)).cpu().numpy(), vox[p2v])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# affinity + random walk
+# ---------------------------------------------------------------------------------------------------------
+def _graph(rng, S, deg):
+    e = set()
+    for u in range(S):
+        for v in rng.choice(S, deg, replace=False):
+            if u != v:
+                e.add((u, int(v)))
+                e.add((int(v), u))
+    return np.array(sorted(e), np.int64)
+
+
+def test_edge_attention_matches_oracle(W, orc):
+    rng = np.random.default_rng(4)
+    S = 700
+    e = _graph(rng, S, 4)
+    e = e[rng.permutation(len(e))]  # the kernel must not rely on sorted edges
+    q, k, v, ecc = (rng.standard_normal((S, 64)).astype(np.float32) for _ in range(4))
+    cen = rng.uniform(0, 5, (S, 3)).astype(np.float32)
+    w1, b1 = rng.standard_normal((16, 3)).astype(np.float32), rng.standard_normal(16).astype(np.float32)
+    w2, b2 = rng.standard_normal((1, 16)).astype(np.float32), rng.standard_normal(1).astype(np.float32)
+    aff_ref, sp_ref = orc.edge_attention(q, k, v, ecc, cen, e[:, 0], e[:, 1], w1, b1, w2, b2)
+    eu, ev = cu(e[:, 0]), cu(e[:, 1])
+    pos = cu(np.concatenate([w1.ravel(), b1, w2.ravel(), b2]))
+    aff, sp = W.edge_attention(cu(q), cu(k), cu(v), cu(ecc), cu(cen), eu, ev, W.SegmentIndex(eu, S), pos)
+    assert rel(aff.cpu().numpy(), aff_ref) < 1e-5
+    assert rel(sp.cpu().numpy(), sp_ref) < 1e-5
+    sums = np.zeros(S)
+    np.add.at(sums, e[:, 0], aff.cpu().numpy())
+    assert np.allclose(sums[np.unique(e[:, 0])], 1.0, atol=1e-5)  # softmax rows sum to one
+
+
+@pytest.mark.parametrize("iterations", [0, 1, 2])
+def test_random_walk_matches_reference_numpy(W, orc, iterations):
+    """Pseudo labels identical, scores to 1e-12 (float64 both sides; only the summation order differs)."""
+    rng = np.random.default_rng(10 + iterations)
+    S, classes = 500, 20
+    e = _graph(rng, S, 4)
+    aff = rng.uniform(0.01, 1, len(e)).astype(np.float32)
+    seed = np.full(S, -100, np.int64)
+    pick = rng.choice(S, 40, replace=False)
+    seed[pick] = rng.integers(0, classes, 40)
+    pred = rng.integers(0, 6, S).astype(np.int64)
+    pred[pick] = np.where(rng.random(40) < 0.8, seed[pick], pred[pick])
+    conf = rng.uniform(0.4, 1.0, S).astype(np.float32)
+    adj = np.zeros((S, S))
+    adj[e[:, 0], e[:, 1]] = 1
+    final_ref, score_ref = orc.weak_label_propagation(seed, adj, conf, pred, orc.dense_affinity(e[:, 0], e[:, 1], aff, S),
+                                                      iterations, classes)
+    pseudo, score = W.random_walk(cu(e[:, 0]), cu(e[:, 1]), cu(aff), cu(seed), cu(pred), cu(conf), classes, iterations)
+    got = pseudo.cpu().numpy().astype(np.float64)
+    assert np.array_equal(got, final_ref), "differs at %s" % np.nonzero(got != final_ref)[0][:10]
+    assert np.abs(score.cpu().numpy() - score_ref).max() < 1e-12
+    assert (final_ref != -100).sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# end to end against the reference's own outputs (tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["scene_b1", "scene_b2"])
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_TOL), ("bf16", 3e-2), ("simt", 2e-5)])
+def test_network_matches_reference_golden(W, golden_dir, name, prec, tol):
+    """The reference Network (run on the reference's spconv CPU kernels) vs the mirror on the CUDA path."""
+    import ast
+    from wsis_b200 import pipeline, synthetic
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    nscene, kw = ast.literal_eval(str(gold["scene_kw"]))
+    batch = synthetic.collate([synthetic.make_scene(9000 + i, **kw) for i in range(nscene)])
+    net = pipeline.build_network(seed=123, device="cpu")
+    g = torch.Generator().manual_seed(7)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75)
+            if m.affine:
+                m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75)
+                m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    chk = np.array([float(p.detach().double().abs().sum()) for p in net.parameters()])
+    # orthogonal_ (LAPACK QR) may round differently on another host CPU, hence 1e-5 and not bit equality
+    assert np.allclose(chk, gold["param_checksum"], rtol=1e-5), "fixed-seed initialisation differs from the reference"
+    net = net.cuda().eval()
+    dbatch, _ = pipeline.to_device(batch)
+    old = W.get_precision()
+    W.set_precision(prec)
+    try:
+        with torch.no_grad():
+            ret, aux = pipeline.forward_batch(net, dbatch)
+    finally:
+        W.set_precision(old)
+    # integer outputs: bit exact
+    assert np.array_equal(aux["voxel_locs"].cpu().numpy(), gold["voxel_locs"])
+    assert np.array_equal(aux["p2v_map"].cpu().numpy(), gold["p2v"])
+    assert np.array_equal(aux["v2p_map"].cpu().numpy(), gold["v2p"])
+    inp = aux["input"]
+    for key in ("subm1", "spconv1", "subm2", "spconv2"):
+        outids, _, pairs, num, _ = inp.indice_dict[key]
+        assert np.array_equal(outids.cpu().numpy(), gold["rb_%s_outids" % key])
+        assert np.array_equal(num.cpu().numpy(), gold["rb_%s_num" % key])
+        if key in ("subm1", "spconv1"):
+            assert np.array_equal(pairs.cpu().numpy(), gold["rb_%s_pairs" % key])
+    assert rel(aux["centers"].cpu().numpy(), gold["centers"]) < 1e-6
+    for k in ("semantic_scores", "sp_semantic_scores", "pred_sp_offset_vectors", "pred_sp_occupancy",
+              "pred_sp_ins_size", "edge_affinity", "sp_discriminative_feats"):
+        assert rel(ret[k].cpu().numpy(), gold["ret_" + k]) < tol, k
+
+
+def test_drop_in_module_api_unfused_equals_fused(W):
+    """SparseSequential's fused BN+ReLU+conv path gives the same result as the module-by-module path."""
+    import spconv
+    from torch import nn
+    rng = np.random.default_rng(3)
+    shape = [19, 18, 17]
+    c = gen_coords(rng, shape, 1500, 1)
+    f = cu(rng.uniform(-1, 1, (len(c), 32)).astype(np.float32))
+    torch.manual_seed(0)
+    seq = spconv.SparseSequential(nn.BatchNorm1d(32, eps=1e-4), nn.ReLU(),
+                                  spconv.SubMConv3d(32, 64, 3, padding=1, bias=False, indice_key="k")).cuda().eval()
+    seq[0].running_mean.uniform_(-0.2, 0.2)
+    seq[0].running_var.uniform_(0.7, 1.3)
+    with torch.no_grad():
+        fused = seq(spconv.SparseConvTensor(f, cu(c), shape, 1)).features
+    x = spconv.SparseConvTensor(f, cu(c), shape, 1)
+    with torch.no_grad():
+        x.features = torch.relu(seq[0](x.features))
+        plain = seq[2](x).features
+    assert float((fused - plain).abs().max()) < FP32_TOL * float(plain.abs().max())
