@@ -90,6 +90,10 @@ __device__ __forceinline__ int64_t hash_find(const unsigned long long *__restric
   }
 }
 
+// tile record geometry (tilemap.cu builds the records, conv_umma.cu consumes them)
+__host__ __device__ __forceinline__ int rec_hdr_bytes(int K) { return 16 * K + ((2 * (K + 1) + 15) & ~15); }
+__host__ __device__ __forceinline__ int rec_stride_bytes(int K) { return (rec_hdr_bytes(K) + 5 * 128 * K + 15) & ~15; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -49,9 +49,9 @@ def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padd
     if indices.dtype != torch.int32:
         indices = indices.int()
     if subm:
-        rb = W.rulebook_subm(indices, spatial_shape, ksize, dilation)
+        rb = W.rulebook_subm(indices, spatial_shape, ksize, dilation, batch_size)
     else:
-        rb, _ = W.rulebook_conv(indices, spatial_shape, ksize, stride, padding, dilation)
+        rb, _ = W.rulebook_conv(indices, spatial_shape, ksize, stride, padding, dilation, batch_size)
     pairs, num = rb.pairs()
     pairs._wsis_rulebook = rb
     return rb.out_coords, pairs, num
@@ -78,11 +78,14 @@ def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_o
     if inverse:
         # features live on the coarse (couple's output) side, result on the fine (couple's input) side
         rb = _rulebook_of(indice_pairs, indice_pair_num, num_activate_out, n_feat, False)
-        map_, flip = rb.nbr_in, 0
+        map_, flip, tiles = rb.nbr_in, 0, rb.tiles_in
     else:
         rb = _rulebook_of(indice_pairs, indice_pair_num, n_feat, num_activate_out, subm)
-        map_, flip = rb.fwd_map()
-    return W.sparse_conv(features, _w3(filters), map_, num_activate_out, flip, False, _prologue, _residual, _packed)
+        (map_, flip), tiles = rb.fwd_map(), rb.tiles_out
+    w3 = _w3(filters)
+    use_tiles = W.get_precision() != "simt" and w3.shape[0] <= 32 and W.umma_supported(w3.shape[1], w3.shape[2])
+    return W.sparse_conv(features, w3, map_, num_activate_out, flip, False, _prologue, _residual, _packed,
+                         tiles=tiles() if use_tiles else None)
 
 
 def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False, subm=False):
@@ -92,13 +95,15 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     w3 = _w3(filters)
     K, Cin, Cout = w3.shape
     n_feat, n_out = features.shape[0], out_bp.shape[0]
+    # dgrad contracts with W[k]^T: Cin_eff = Cout, Cout_eff = Cin
+    use_tiles = W.get_precision() != "simt" and K <= 32 and W.umma_supported(Cout, Cin)
     if inverse:
         rb = _rulebook_of(indice_pairs, indice_pair_num, n_out, n_feat, False)
-        din = W.sparse_conv(out_bp, w3, rb.nbr_out, n_feat, 0, True)
+        din = W.sparse_conv(out_bp, w3, rb.nbr_out, n_feat, 0, True, tiles=rb.tiles_out() if use_tiles else None)
         dw = W.sparse_conv_wgrad(features, rb.nbr_in, n_out, 0, out_bp, K, Cin, Cout)
     else:
         rb = _rulebook_of(indice_pairs, indice_pair_num, n_feat, n_out, subm)
         fmap, fflip = rb.fwd_map()
-        din = W.sparse_conv(out_bp, w3, rb.nbr_in, n_feat, 0, True)
+        din = W.sparse_conv(out_bp, w3, rb.nbr_in, n_feat, 0, True, tiles=rb.tiles_in() if use_tiles else None)
         dw = W.sparse_conv_wgrad(features, fmap, n_out, fflip, out_bp, K, Cin, Cout)
     return din, dw.view(filters.shape)

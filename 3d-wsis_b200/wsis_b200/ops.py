@@ -68,16 +68,78 @@ def launch_count():
 # ---------------------------------------------------------------------------------------------------------
 # rulebook
 # ---------------------------------------------------------------------------------------------------------
+def spatial_order(coords, spatial_shape, batch_size):
+    """Morton-curve order of a coordinate set int32[N,4] -> int32[tile_pad(N)] (row ids, -1 padded).  Cached on
+    the coords tensor: every rulebook of a level shares it."""
+    cached = getattr(coords, "_wsis_order", None)
+    if cached is not None:
+        return cached
+    N = coords.shape[0]
+    dev = coords.device
+    n_pad = lib().value("wsis_tile_pad", N)
+    order = torch.empty((max(n_pad, 1),), dtype=torch.int32, device=dev)
+    if N > 0:
+        ws = _bytes(lib().value("wsis_spatial_order_ws_bytes", N), dev)
+        lib().call("wsis_spatial_order", _ptr(coords), N, _c3(_i3(list(spatial_shape))), int(batch_size), _ptr(order),
+                   _ptr(ws), _stream())
+    try:
+        coords._wsis_order = order
+    except Exception:  # noqa: BLE001  (tensor subclasses that refuse attributes)
+        pass
+    return order
+
+
+def identity_order(n, device):
+    n_pad = lib().value("wsis_tile_pad", n)
+    order = torch.empty((max(n_pad, 1),), dtype=torch.int32, device=device)
+    if n > 0:
+        lib().call("wsis_identity_order", n, _ptr(order), _stream())
+    return order
+
+
+class TileMap:
+    """A neighbour map in the form conv_umma consumes: destination rows in tiles of 128 along `order`, one compact
+    record per tile (include/wsis_b200.h, wsis_tile_records)."""
+
+    def __init__(self, map_, n_dst, flip, order):
+        K = map_.shape[1]
+        self.K, self.n_dst = K, n_dst
+        self.order = order
+        self.num_tiles = lib().value("wsis_tile_pad", n_dst) // 128
+        self.stride = lib().value("wsis_tile_record_stride", K)
+        # fixed-stride records (only rec_bytes[t] of each are ever read): no size scan, no host sync
+        self.records = _bytes(self.num_tiles * self.stride, map_.device)
+        self.rec_bytes = torch.empty((max(self.num_tiles, 1),), dtype=torch.int32, device=map_.device)
+        if n_dst > 0:
+            lib().call("wsis_tile_records", _ptr(map_), n_dst, K, int(flip), _ptr(order), _ptr(self.records),
+                       _ptr(self.rec_bytes), _stream())
+
+
+def _tiles_of(map_, n_dst, flip):
+    """Identity-order TileMap for callers that bring a bare neighbour map (cached on the map tensor)."""
+    cache = getattr(map_, "_wsis_tiles", None)
+    if cache is None:
+        cache = {}
+        map_._wsis_tiles = cache
+    if flip not in cache:
+        cache[flip] = TileMap(map_, n_dst, flip, identity_order(n_dst, map_.device))
+    return cache[flip]
+
+
 class Rulebook:
     """Output-stationary rulebook: nbr_in[i,k] = out row, nbr_out[o,k] = in row (see include/wsis_b200.h).
 
     Replaces the (indice_pairs, indice_pair_num) pair of spconv_ops.h:27-137; `pairs()` still materialises the
-    reference-format tensors (conv.py:152 stores them in indice_dict)."""
+    reference-format tensors (conv.py:152 stores them in indice_dict).  `tiles_out()` / `tiles_in()` are the
+    spatially tiled maps the tensor-core kernel walks (destination = output side / input side)."""
 
-    def __init__(self, kind, K, n_in, n_out, nbr_in, nbr_out, out_coords):
+    def __init__(self, kind, K, n_in, n_out, nbr_in, nbr_out, out_coords, in_coords=None, in_shape=None,
+                 out_shape=None, batch_size=1):
         self.kind, self.K, self.n_in, self.n_out = kind, K, n_in, n_out
         self.nbr_in, self.nbr_out, self.out_coords = nbr_in, nbr_out, out_coords
+        self.in_coords, self.in_shape, self.out_shape, self.batch_size = in_coords, in_shape, out_shape, batch_size
         self._pairs = None
+        self._tiles = {}
 
     def pairs(self):
         if self._pairs is None:
@@ -102,8 +164,28 @@ class Rulebook:
     def bwd_map(self):  # maps rows of the conv INPUT side to rows of the OUTPUT side
         return (self.nbr_in, 0)
 
+    def _order(self, side):
+        coords, shape = (self.out_coords, self.out_shape) if side == "out" else (self.in_coords, self.in_shape)
+        n = self.n_out if side == "out" else self.n_in
+        if coords is None or shape is None:
+            return identity_order(n, self.nbr_in.device)
+        return spatial_order(coords, shape, self.batch_size)
 
-def rulebook_subm(indices, spatial_shape, ksize=3, dilation=1):
+    def tiles_out(self):
+        """Destination = the conv's output rows (forward of subm / strided conv, dgrad of the inverse conv)."""
+        if "out" not in self._tiles:
+            m, flip = self.fwd_map()
+            self._tiles["out"] = TileMap(m, self.n_out, flip, self._order("out"))
+        return self._tiles["out"]
+
+    def tiles_in(self):
+        """Destination = the conv's input rows (dgrad of subm / strided conv, forward of the inverse conv)."""
+        if "in" not in self._tiles:
+            self._tiles["in"] = TileMap(self.nbr_in, self.n_in, 0, self._order("in"))
+        return self._tiles["in"]
+
+
+def rulebook_subm(indices, spatial_shape, ksize=3, dilation=1, batch_size=None):
     """Submanifold rulebook: replaces getIndicePair<3> with subM=1 (spconv_ops.h:86-102)."""
     indices = _cuda(indices, "indices")
     assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4
@@ -119,7 +201,12 @@ def rulebook_subm(indices, spatial_shape, ksize=3, dilation=1):
         vals = torch.empty((slots,), dtype=torch.int32, device=dev)
         lib().call("wsis_rulebook_subm", _ptr(indices), N, _c3(ks), _c3(dil), _c3(shape), _ptr(keys), _ptr(vals), slots,
                    _ptr(nbr), _stream())
-    return Rulebook("subm", K, N, N, nbr, None, indices)
+    return Rulebook("subm", K, N, N, nbr, None, indices, indices, shape, shape, _batch_of(batch_size))
+
+
+def _batch_of(batch_size):
+    # the Morton key reserves ceil(log2(batch)) bits; without a hint allow for 65536 scenes per batch
+    return 65536 if batch_size is None else max(int(batch_size), 1)
 
 
 def conv_output_shape(spatial_shape, ksize, stride, padding, dilation):
@@ -128,7 +215,7 @@ def conv_output_shape(spatial_shape, ksize, stride, padding, dilation):
     return [(s[i] + 2 * p[i] - d[i] * (k[i] - 1) - 1) // st[i] + 1 for i in range(3)]
 
 
-def rulebook_conv(indices, spatial_shape, ksize, stride, padding=0, dilation=1):
+def rulebook_conv(indices, spatial_shape, ksize, stride, padding=0, dilation=1, batch_size=None):
     """Strided sparse-conv rulebook: replaces getIndicePair<3> with subM=0 (spconv_ops.h:103-136).
     One host sync to learn the output count (the reference syncs for the same reason, :126-135)."""
     indices = _cuda(indices, "indices")
@@ -162,7 +249,8 @@ def rulebook_conv(indices, spatial_shape, ksize, stride, padding=0, dilation=1):
     slot_rank = torch.empty((slots,), dtype=torch.int32, device=dev)
     lib().call("wsis_rulebook_conv_fill", _ptr(indices), N, K, _ptr(keys), _ptr(vals), slots, _ptr(nbr_in), _ptr(rank),
                _ptr(slot_rank), n_out, _ptr(out_coords), _ptr(nbr_out), _stream())
-    return Rulebook("conv", K, N, n_out, nbr_in, nbr_out, out_coords), oshape
+    return Rulebook("conv", K, N, n_out, nbr_in, nbr_out, out_coords, indices, _i3(list(spatial_shape)), oshape,
+                    _batch_of(batch_size)), oshape
 
 
 def rulebook_from_pairs(pairs, num, n_in, n_out, subm):
@@ -211,10 +299,11 @@ def umma_supported(Cin, Cout):
 
 
 def sparse_conv(src, weight3, map_, n_dst, flip, transpose_w=False, prologue=None, residual=None, packed=None,
-                precision=None):
+                precision=None, tiles=None):
     """dst[r] = residual[r] + sum_k prologue(src[map[r,k']]) @ W[k]  (W[k]^T when transpose_w).
 
-    src f32[n_src, Cin]; weight3 f32[K, Cin_w, Cout_w]; map_ int32[n_dst, K]."""
+    src f32[n_src, Cin]; weight3 f32[K, Cin_w, Cout_w]; map_ int32[n_dst, K]; `tiles` = the TileMap of
+    (map_, flip) when the caller has one (Rulebook.tiles_out()/tiles_in()), else an identity-order one is built."""
     src = _cuda(src, "features")
     if src.dtype != torch.float32:
         raise RuntimeError("wsis_b200: features must be float32, got %s" % src.dtype)
@@ -243,12 +332,15 @@ def sparse_conv(src, weight3, map_, n_dst, flip, transpose_w=False, prologue=Non
         residual = residual.contiguous()
         assert residual.shape == dst.shape and residual.dtype == torch.float32
     precision = precision or _PRECISION
-    if precision != "simt" and umma_supported(Cin, Cout):
+    if precision != "simt" and K <= 32 and umma_supported(Cin, Cout):
         prec = 3 if precision == "fp32" else 1
         packed = packed if packed is not None else PackedWeights()
         buf = packed.get(weight3, bool(transpose_w), prec)
-        lib().call("wsis_conv_umma", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(buf), Cin, Cout, prec,
-                   _ptr(scale), _ptr(shift), int(relu), _ptr(residual), _ptr(dst), _stream())
+        tiles = tiles if tiles is not None else _tiles_of(map_, n_dst, int(flip))
+        assert tiles.n_dst == n_dst and tiles.K == K
+        lib().call("wsis_conv_umma", _ptr(src), _ptr(tiles.records), _ptr(tiles.rec_bytes), _ptr(tiles.order),
+                   tiles.num_tiles, K, _ptr(buf), Cin, Cout, prec, _ptr(scale), _ptr(shift), int(relu), _ptr(residual),
+                   _ptr(dst), _stream())
     else:
         lib().call("wsis_conv_simt", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(weight3), int(transpose_w), Cin,
                    Cout, _ptr(scale), _ptr(shift), int(relu), _ptr(residual), _ptr(dst), _stream())

@@ -115,15 +115,35 @@ int wsis_conv_simt(const float *src, const int32_t *map, int64_t n_dst, int K, i
                    int transpose_w, int Cin, int Cout, const float *in_scale, const float *in_shift, int in_relu,
                    const float *residual, float *dst, wsis_stream_t stream);
 
-/* tcgen05 tensor-core path.  precision: 1 = bf16 operands (1e-2 contract), 3 = bf16x3 split operands with
- * fp32 accumulation in TMEM (1e-4 contract).  Requires Cin % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 256. */
+/* Spatial tiling (no reference equivalent: the reference walks pairs in arrival order, indice.cu.h:171-208).
+ * wsis_tile_pad(n) = n rounded up to a multiple of 128.  wsis_spatial_order sorts a coordinate set along a
+ * Morton curve (batch-major): order int32[wsis_tile_pad(N)] = row ids in curve order, padded with -1.
+ * wsis_identity_order gives the trivial order for callers without coordinates.
+ * wsis_tile_records compacts a neighbour map into per-tile RECORDS, the only form of the rulebook the tensor-core
+ * kernel reads: for tile t (destination rows order[128t .. 128t+127]) and `m[r,k] = map[order[..], flip ? K-1-k : k]`
+ *   valid[K][4] u32 | start[K+1] u16 | idx[P] i32 (source rows) | slot[P] u8 (tile slots), P = pairs of the tile,
+ * at a fixed stride wsis_tile_record_stride(K) (worst case P = 128 K), of which rec_bytes[t] bytes are meaningful.
+ * records: uint8[num_tiles * stride] (16-byte aligned), rec_bytes: int32[num_tiles].  K <= 32. */
+int64_t wsis_tile_pad(int64_t n);
+int64_t wsis_spatial_order_ws_bytes(int64_t N);
+int wsis_spatial_order(const int32_t *coords, int64_t N, const int32_t spatial_shape[3], int batch_size,
+                       int32_t *order, void *ws, wsis_stream_t stream);
+int wsis_identity_order(int64_t N, int32_t *order, wsis_stream_t stream);
+int64_t wsis_tile_record_stride(int K);
+int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const int32_t *order, void *records,
+                      int32_t *rec_bytes, wsis_stream_t stream);
+
+/* tcgen05 tensor-core path over tile records (num_tiles = wsis_tile_pad(n_dst)/128).  precision: 1 = bf16 operands
+ * (1e-2 contract), 3 = bf16x3 split operands with fp32 accumulation in TMEM (1e-4 contract).
+ * Requires Cin % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 256, K <= 32. */
 int wsis_conv_umma_supported(int Cin, int Cout);
 int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision);
 int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
                            wsis_stream_t stream);
-int wsis_conv_umma(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const void *packed,
-                   int Cin, int Cout, int precision, const float *in_scale, const float *in_shift, int in_relu,
-                   const float *residual, float *dst, wsis_stream_t stream);
+int wsis_conv_umma(const float *src, const void *records, const int32_t *rec_bytes, const int32_t *order,
+                   int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
+                   const float *in_scale, const float *in_shift, int in_relu, const float *residual, float *dst,
+                   wsis_stream_t stream);
 
 /* dW[k] = sum_r prologue(src[map[r,k']])^T . g[r]   (fp32, dW is zeroed by the call). */
 int wsis_conv_wgrad(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const float *g, int Cin,

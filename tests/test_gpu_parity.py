@@ -505,3 +505,125 @@ def test_drop_in_module_api_unfused_equals_fused(W):
         x.features = torch.relu(seq[0](x.features))
         plain = seq[2](x).features
     assert float((fused - plain).abs().max()) < FP32_TOL * float(plain.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# spatial tiling (tilemap.cu) and the tiled tensor-core kernel
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,bs,shape", [(1, 1, [8, 8, 8]), (127, 1, [19, 18, 17]), (128, 2, [19, 18, 17]),
+                                        (5000, 3, [40, 36, 32]), (60000, 4, [400, 300, 128])])
+def test_spatial_order_is_a_local_permutation(W, n, bs, shape):
+    rng = np.random.default_rng(n)
+    c = np.concatenate([rng.integers(0, bs, (n, 1)), rng.integers(0, shape[0], (n, 1)), rng.integers(0, shape[1], (n, 1)),
+                        rng.integers(0, min(shape[2], 4), (n, 1))], 1).astype(np.int32)   # a thin slab = a surface
+    order = W.spatial_order(cu(c), shape, bs).cpu().numpy()
+    n_pad = (n + 127) // 128 * 128
+    assert order.shape[0] == max(n_pad, 1) or order.shape[0] == n_pad
+    assert np.array_equal(np.sort(order[:n]), np.arange(n)) and np.all(order[n:n_pad] == -1)
+    s = c[order[:n]]
+    assert np.all(np.diff(s[:, 0]) >= 0)                                  # batch-major
+    if n >= 5000:
+        step = np.abs(np.diff(s[:, 1:].astype(np.int64), axis=0)).sum(1)
+        rnd = np.abs(np.diff(c[:, 1:].astype(np.int64), axis=0)).sum(1)
+        assert np.median(step) * 8 < np.median(rnd)                       # curve order is spatially local
+
+
+def _decode_records(t, K):
+    """Tile records (include/wsis_b200.h: wsis_tile_records) -> dense int32[n_pad, K] map, checking the layout."""
+    rec = t.records.cpu().numpy()
+    nbytes = t.rec_bytes.cpu().numpy()
+    hdr = 16 * K + ((2 * (K + 1) + 15) // 16) * 16
+    out = np.full((t.num_tiles * 128, K), -1, np.int32)
+    for ti in range(t.num_tiles):
+        r = rec[ti * t.stride:(ti + 1) * t.stride]
+        valid = r[:16 * K].view(np.uint32).reshape(K, 4)
+        start = r[16 * K:16 * K + 2 * (K + 1)].view(np.uint16).astype(np.int64)
+        P = int(start[K])
+        assert nbytes[ti] == (hdr + 5 * P + 15) // 16 * 16 and start[0] == 0 and np.all(np.diff(start) >= 0)
+        idx = r[hdr:hdr + 4 * P].view(np.int32)
+        slot = r[hdr + 4 * P:hdr + 5 * P]
+        for k in range(K):
+            sl = slot[start[k]:start[k + 1]].astype(np.int64)
+            assert np.all(np.diff(sl) > 0)
+            bits = np.zeros(128, bool)
+            bits[sl] = True
+            assert np.array_equal(np.unpackbits(valid[k].view(np.uint8), bitorder="little").astype(bool), bits)
+            out[ti * 128 + sl, k] = idx[start[k]:start[k + 1]]
+    return out
+
+
+@pytest.mark.parametrize("K", [27, 8, 1])
+def test_tile_records_match_numpy(W, K):
+    rng = np.random.default_rng(2 + K)
+    n = 1000
+    m = rng.integers(-1, n, (n, K)).astype(np.int32)
+    m[rng.random((n, K)) < 0.6] = -1
+    m[130:260] = -1                                          # a tile without any entry
+    m[300:428] = rng.integers(0, n, (128, K))                # a full tile (worst-case record size)
+    order = np.concatenate([rng.permutation(n), np.full(24, -1)]).astype(np.int32)
+    for flip in (0, 1):
+        t = W.TileMap(cu(m), n, flip, cu(order))
+        exp = np.full((1024, K), -1, np.int32)
+        exp[:n] = m[order[:n]][:, ::-1] if flip else m[order[:n]]
+        assert t.num_tiles == 8 and np.array_equal(_decode_records(t, K), exp)
+
+
+@pytest.mark.parametrize("npts,bs", [(100, 1), (128, 1), (3000, 2), (12000, 2)])
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_subm_conv_morton_tiles(W, orc, npts, bs, prec, tol):
+    """The production path: Morton-ordered tiles, fused BN+ReLU prologue and residual epilogue; > 148 tiles in the
+    largest case so every CTA walks several tiles through the double-buffered map/accumulator."""
+    rng = np.random.default_rng(npts)
+    shape = [40, 36, 32]
+    c = gen_coords(rng, shape, npts, bs)
+    cin, cout = 64, 32
+    f = rng.uniform(-1, 1, (len(c), cin)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (27, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cin).astype(np.float32)
+    shift = rng.uniform(-0.3, 0.3, cin).astype(np.float32)
+    res = rng.uniform(-1, 1, (len(c), cout)).astype(np.float32)
+    pairs, num = orc.rulebook_subm(c, bs, shape, 3, 1)
+    ref = orc.indice_conv(np.maximum(f * scale + shift, 0), w, pairs, num, len(c)) + res
+    rb = W.rulebook_subm(cu(c), shape, 3, 1, batch_size=bs)
+    out = W.sparse_conv(cu(f), cu(w), rb.nbr_in, len(c), 1, prologue=(cu(scale), cu(shift), 1), residual=cu(res),
+                        precision=prec, tiles=rb.tiles_out())
+    assert rel(out.cpu().numpy(), ref) < tol
+    # dgrad through the input-side tiles: din = sum_k g[nbr_in[i,k]] W[k]^T
+    g = rng.uniform(-1, 1, (len(c), cout)).astype(np.float32)
+    din_ref, _ = orc.indice_conv_backward(f, w, g, pairs, num)
+    din = W.sparse_conv(cu(g), cu(w), rb.nbr_in, len(c), 0, True, precision=prec, tiles=rb.tiles_in())
+    assert rel(din.cpu().numpy(), din_ref) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_strided_and_inverse_conv_morton_tiles(W, orc, prec, tol):
+    rng = np.random.default_rng(16)
+    shape = [44, 38, 30]
+    c = gen_coords(rng, shape, 9000, 2)
+    f = rng.uniform(-1, 1, (len(c), 32)).astype(np.float32)
+    wd = rng.uniform(-1, 1, (8, 32, 64)).astype(np.float32) / 6
+    wu = rng.uniform(-1, 1, (8, 64, 32)).astype(np.float32) / 8
+    oc, pairs, num, _ = orc.rulebook_conv(c, 2, shape, 2, 2, 0, 1)
+    down_ref = orc.indice_conv(f, wd, pairs, num, len(oc))
+    up_ref = orc.indice_conv(down_ref, wu, pairs, num, len(c), inverse=True)
+    rb, _ = W.rulebook_conv(cu(c), shape, 2, 2, 0, 1, batch_size=2)
+    down = W.sparse_conv(cu(f), cu(wd), rb.nbr_out, rb.n_out, 0, precision=prec, tiles=rb.tiles_out())
+    assert rel(down.cpu().numpy(), down_ref) < tol
+    up = W.sparse_conv(cu(down_ref), cu(wu), rb.nbr_in, rb.n_in, 0, precision=prec, tiles=rb.tiles_in())
+    assert rel(up.cpu().numpy(), up_ref) < tol
+
+
+def test_conv_tile_without_any_neighbour(W):
+    """A whole tile whose map rows are all -1 must still produce zeros (+ residual), not stale accumulator data."""
+    rng = np.random.default_rng(4)
+    n, K, cin, cout = 384, 27, 32, 32
+    m = np.full((n, K), -1, np.int32)
+    m[128:256, 13] = np.arange(128, 256)                       # only the middle tile has neighbours (identity)
+    f = rng.uniform(-1, 1, (n, cin)).astype(np.float32)
+    w = rng.uniform(-1, 1, (K, cin, cout)).astype(np.float32)
+    res = rng.uniform(-1, 1, (n, cout)).astype(np.float32)
+    out = W.sparse_conv(cu(f), cu(w), cu(m), n, 0, residual=cu(res), precision="fp32").cpu().numpy()
+    exp = res.copy()
+    exp[128:256] += f[128:256] @ w[13]
+    assert rel(out, exp) < FP32_TOL
+    assert np.array_equal(out[:128], res[:128]) and np.array_equal(out[256:], res[256:])
