@@ -38,12 +38,12 @@ namespace wsis {
 namespace umma {
 
 constexpr int kTileM = 128;
-constexpr int kKB = 32;                  // channels per pipeline unit (64 bytes of bf16 = one swizzle-64 row)
+constexpr int kKB = 32;                    // channels per pipeline unit (64 bytes of bf16 = one swizzle-64 row)
 constexpr int kABlockBytes = kTileM * 64;  // 8 KB
-constexpr int kEpiWarps = 4, kLoadWarps = 8;
-constexpr int kMmaWarps = 2;
-constexpr int kThreads = (kEpiWarps + kLoadWarps + kMmaWarps + 1) * 32;  // 480
-constexpr int kLoaderThreads = kLoadWarps * 32;
+constexpr int kEpiWarps = 4, kGatherWarps = 4, kBuildWarps = 6, kMmaWarps = 2, kProdWarps = 2;
+constexpr int kThreads = (kEpiWarps + kGatherWarps + kBuildWarps + kMmaWarps + kProdWarps) * 32;  // 576
+constexpr int kNRec = 2;    // tile records in flight
+constexpr int kRcap = 256;  // rows of one row-cache buffer (a surface tile reads ~160-230 distinct rows)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -138,17 +138,56 @@ __host__ __device__ __forceinline__ uint32_t sw64(uint32_t row, uint32_t c16) {
 
 struct Params {
   const float *src;
-  const uint8_t *recs;       // tile records at stride rec_stride_bytes(K) (tilemap.cu)
-  const int32_t *rec_bytes;  // [num_tiles] bytes of each record actually used
-  const int32_t *order;      // [num_tiles*128] destination row of each tile slot (-1 = padding)
+  const uint8_t *recs;    // entry records at stride rec_stride_bytes(K) (tilemap.cu)
+  const int32_t *uidx;    // [num_tiles][128 K] distinct source rows of each tile
+  const int4 *meta;       // [num_tiles] {record bytes, nU, active-offset mask, P}
+  const int32_t *order;   // [num_tiles*128] destination row of each tile slot (-1 = padding)
   const uint8_t *packed;
   const float *in_scale, *in_shift, *residual;
   float *dst;
-  int K, Cin, Cout, in_relu, nstage, nrec, nlw, nacc, nmma, tmem_cols;
+  int K, Cin, Cout, KB, in_relu, vec4;
+  int lna, lnw, nrc, nacc, nmma, tmem_cols;  // A ring = 1 << lna stages, W ring = 1 << lnw stages
   int64_t num_tiles;
 };
 
-constexpr uint32_t kHdrLast = 1u;
+// relu?(x * sc + sh) -> bf16 hi (part 0) or bf16 mid = bf16(y - hi) (part 1), two values per 32-bit word
+__device__ __forceinline__ uint32_t split2(float a, float b, int part) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  uint32_t hv = *reinterpret_cast<uint32_t *>(&h);
+  if (part == 0) return hv;
+  // bf16 -> fp32 is a 16-bit shift: the residual y - hi is exact in fp32
+  __nv_bfloat162 m = __floats2bfloat162_rn(a - __uint_as_float(hv << 16), b - __uint_as_float(hv & 0xffff0000u));
+  return *reinterpret_cast<uint32_t *>(&m);
+}
+
+__device__ __forceinline__ float4 load_row4(const Params &p, int32_t row, int c0) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float *s = p.src + (int64_t)row * p.Cin + c0;
+  if (p.vec4) {
+    if (c0 < p.Cin) v = __ldg(reinterpret_cast<const float4 *>(s));
+  } else {  // narrow or unaligned rows (the 6-channel input layer): guarded scalar loads, zero padding
+    if (c0 < p.Cin) v.x = __ldg(s);
+    if (c0 + 1 < p.Cin) v.y = __ldg(s + 1);
+    if (c0 + 2 < p.Cin) v.z = __ldg(s + 2);
+    if (c0 + 3 < p.Cin) v.w = __ldg(s + 3);
+  }
+  return v;
+}
+
+__device__ __forceinline__ float4 prologue4(float4 x, float4 sc, float4 sh, int relu) {
+  float4 y = make_float4(fmaf(x.x, sc.x, sh.x), fmaf(x.y, sc.y, sh.y), fmaf(x.z, sc.z, sh.z), fmaf(x.w, sc.w, sh.w));
+  if (relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+  return y;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 template <int NS>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) {
@@ -156,52 +195,71 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
   uint8_t *sm = smem_raw + pad;
-  const int KB = p.Cin / kKB;
-  const uint32_t a_bytes = NS * kABlockBytes;
+  const int KB = p.KB;
+  const uint32_t na = 1u << p.lna, nw = 1u << p.lnw;
+  constexpr uint32_t a_stage = NS * kABlockBytes;
   const uint32_t b_block = (uint32_t)p.Cout * 64u;
-  const uint32_t b_bytes = NS * b_block;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t w_stage = NS * b_block;
+  constexpr uint32_t row_b = NS * 64;  // one row-cache row: 32 channels of bf16 hi (+ 32 of bf16 mid)
+  constexpr uint32_t rc_buf = kRcap * row_b;
   const uint32_t rec_stride = (uint32_t)rec_stride_bytes(p.K);
+  const uint32_t rec_buf = rec_stride + kRcap * 4;  // entry record + the first kRcap unique rows
   const uint32_t hdr_bytes = (uint32_t)rec_hdr_bytes(p.K);
-  uint8_t *tail = sm + (size_t)p.nstage * stage_bytes;
-  uint8_t *s_rec = tail;  // [nrec][rec_stride], filled by bulk copies
-  float *s_scale = reinterpret_cast<float *>(tail + (size_t)p.nrec * rec_stride);
-  float *s_shift = s_scale + p.Cin;
-  uint4 *s_smask = reinterpret_cast<uint4 *>(s_shift + p.Cin);   // [16] valid-slot mask of the unit in each stage
-  uint32_t *s_hdr = reinterpret_cast<uint32_t *>(s_smask + 16);  // [16]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_hdr + 16);
-  // bars: full[nstage], empty[nstage], acc_full[2], acc_empty[2], rec_full[nrec], rec_empty[nrec]
+  uint8_t *s_a = sm;                                  // [na][NS][128 x 64 B swizzled]  A operands
+  uint8_t *s_w = s_a + (size_t)na * a_stage;          // [nw][NS][Cout x 64 B swizzled] weight blocks (bulk copies)
+  uint8_t *s_rc = s_w + (size_t)nw * w_stage;         // [nrc][kRcap][row_b]            converted source rows
+  uint8_t *s_rec = s_rc + (size_t)p.nrc * rc_buf;     // [kNRec][rec_buf]               tile records (bulk copies)
+  float *s_scale = reinterpret_cast<float *>(s_rec + (size_t)kNRec * rec_buf);
+  float *s_shift = s_scale + KB * kKB;
+  uint4 *s_smask = reinterpret_cast<uint4 *>(s_shift + KB * kKB);  // [na] valid-slot mask of the unit in each A stage
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_smask + na);
   const uint32_t bar0 = smem_u32(bars);
-  auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (p.nstage + s); };
-  auto accf_bar = [&](uint32_t s) { return bar0 + 8u * (2 * p.nstage + s); };
-  auto acce_bar = [&](uint32_t s) { return bar0 + 8u * (2 * p.nstage + 2 + s); };
-  auto recf_bar = [&](uint32_t s) { return bar0 + 8u * (2 * p.nstage + 4 + s); };
-  auto rece_bar = [&](uint32_t s) { return bar0 + 8u * (2 * p.nstage + 4 + p.nrec + s); };
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.nstage + 4 + 2 * p.nrec);
+  auto afull_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto aempty_bar = [&](uint32_t s) { return bar0 + 8u * (na + s); };
+  auto wfull_bar = [&](uint32_t s) { return bar0 + 8u * (2 * na + s); };
+  auto wempty_bar = [&](uint32_t s) { return bar0 + 8u * (2 * na + nw + s); };
+  const uint32_t bar1 = bar0 + 8u * (2 * na + 2 * nw);
+  auto rcf_bar = [&](uint32_t s) { return bar1 + 8u * s; };
+  auto rce_bar = [&](uint32_t s) { return bar1 + 8u * (p.nrc + s); };
+  const uint32_t bar2 = bar1 + 8u * (2 * p.nrc);
+  auto recf_bar = [&](uint32_t s) { return bar2 + 8u * s; };
+  auto rece_bar = [&](uint32_t s) { return bar2 + 8u * (kNRec + s); };
+  auto accf_bar = [&](uint32_t s) { return bar2 + 8u * (2 * kNRec + s); };
+  auto acce_bar = [&](uint32_t s) { return bar2 + 8u * (2 * kNRec + 2 + s); };
+  const uint32_t nbars = 2 * na + 2 * nw + 2 * p.nrc + 2 * kNRec + 4;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + nbars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int c = tid; c < p.Cin; c += kThreads) {
-    s_scale[c] = p.in_scale ? p.in_scale[c] : 1.f;
-    s_shift[c] = p.in_shift ? p.in_shift[c] : 0.f;
+  for (int c = tid; c < KB * kKB; c += kThreads) {  // channels padded up to the unit width contribute exact zeros
+    s_scale[c] = c < p.Cin ? (p.in_scale ? p.in_scale[c] : 1.f) : 0.f;
+    s_shift[c] = c < p.Cin ? (p.in_shift ? p.in_shift[c] : 0.f) : 0.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < p.nstage; ++s) {
-      mbar_init(full_bar(s), 2);  // the owning loader warp: expect_tx arrive (weights) + arrive (A rows written)
-      mbar_init(empty_bar(s), 1);
+    for (uint32_t s = 0; s < na; ++s) {
+      mbar_init(afull_bar(s), 1);   // the builder warp of the unit
+      mbar_init(aempty_bar(s), 1);  // tcgen05.commit
+    }
+    for (uint32_t s = 0; s < nw; ++s) {
+      mbar_init(wfull_bar(s), 1);   // expect_tx arrive of the weight producer (+ the bulk copy's bytes)
+      mbar_init(wempty_bar(s), 1);  // tcgen05.commit
+    }
+    for (int s = 0; s < p.nrc; ++s) {
+      mbar_init(rcf_bar(s), kGatherWarps);
+      mbar_init(rce_bar(s), kBuildWarps);
+    }
+    for (int s = 0; s < kNRec; ++s) {
+      mbar_init(recf_bar(s), 1);
+      mbar_init(rece_bar(s), kGatherWarps + kBuildWarps);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(accf_bar(s), p.nmma);
       mbar_init(acce_bar(s), kEpiWarps * 32);
     }
-    for (int s = 0; s < p.nrec; ++s) {
-      mbar_init(recf_bar(s), 1);
-      mbar_init(rece_bar(s), kLoadWarps);
-    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kEpiWarps + kLoadWarps) {  // the first MMA warp owns the TMEM allocation
+  constexpr int kMmaWarp0 = kEpiWarps + kGatherWarps + kBuildWarps;
+  if (warp == kMmaWarp0) {  // the first MMA warp owns the TMEM allocation
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -268,159 +326,175 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         aph ^= 1;
       }
     }
-  } else if (warp < kEpiWarps + kLoadWarps) {
-    // ===================== loaders: one WARP per pipeline unit =====================
-    // The CTA runs nmma independent PIPELINES (one MMA issuer, its own stage ring and its own loader warps each).
-    // Unit g of this CTA (counted across its tiles) belongs to pipeline g % nmma; inside a pipeline the j-th unit
-    // lives in ring stage j % nsp and is gathered by the pipeline's loader warp j % nlp, so several units are
-    // gathered concurrently and the per-unit protocol cost (barrier wait, fence, arrive) is paid by one warp, not
-    // by all.  nlp <= nsp: a warp moves from unit j to j + nlp, and a parity wait on the stage's empty barrier is
-    // only unambiguous while that is at most one ring generation ahead of the (in-order) commits of the issuer.
-    // 8 lanes cover one source row slice (32 channels = 128 B), 4 rows per load instruction, up to 8 load
-    // instructions in flight per lane.
-    const int lw = warp - kEpiWarps;
-    const int chunk = lane & 7;  // 4 fp32 channels = 8 bytes of bf16
-    const int sub4 = lane >> 3;  // entry within a group of 4
-    const uint32_t c16 = chunk >> 1, sub = (chunk & 1) * 8;
-    uint32_t it = 0;
-    uint32_t g0 = 0;  // units of this CTA before the current tile
+  } else if (warp < kEpiWarps + kGatherWarps) {
+    // ===================== gatherers: every distinct source row of a tile is fetched ONCE =====================
+    // One PASS = (tile, 32-channel block kb): the 128-byte slices of the tile's unique rows are loaded with
+    // 16-byte loads (8 lanes per row, 8 rows per lane in flight), the fused eval-BatchNorm+ReLU prologue is applied,
+    // the result is split fp32 -> bf16 hi (+ bf16 mid) and parked in a row-cache buffer.  The builders then
+    // assemble the per-offset A operands from shared memory, so HBM/L2 see each row once per tile instead of once
+    // per (row, offset) entry, and the loads of up to nrc passes are in flight ahead of the tensor pipe.
+    const int gt = (warp - kEpiWarps) * 32 + lane;
+    const int rsub = gt >> 3, chunk = gt & 7;
+    uint32_t it = 0, q = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t rb = it % p.nrec;
-      mbar_wait(recf_bar(rb), (it / p.nrec) & 1);
-      const uint8_t *rec = s_rec + (size_t)rb * rec_stride;
-      const uint16_t *start = reinterpret_cast<const uint16_t *>(rec + 16 * p.K);
-      const int P = start[p.K];
-      const int32_t *ridx = reinterpret_cast<const int32_t *>(rec + hdr_bytes);
-      const uint8_t *rslot = rec + hdr_bytes + 4 * P;
-      // active offsets of the tile (those with at least one entry); a tile without any entry still sends one
-      // all-lanes-off unit through the pipeline so that its rows are written (zeros + residual)
-      uint32_t mask = __ballot_sync(0xffffffffu, lane < p.K && start[lane + 1] > start[lane]);
-      if (mask == 0) mask = 1u;
-      const uint32_t nreal = (uint32_t)__popc(mask) * KB;
-      // every MMA issuer gets the same number of units per tile: pad with empty units (no lanes, no weights)
-      const uint32_t nunits = (nreal + p.nmma - 1) / p.nmma * p.nmma;
-      // my units: pipeline pi = lw % nmma, loader slot pc = lw / nmma (slots >= nlp only keep the record barriers
-      // moving); the tile's t-th unit of the pipeline is its j = j0 + t -th overall
-      const uint32_t P_ = (uint32_t)p.nmma, nlp = (uint32_t)p.nlw, nsp = (uint32_t)p.nstage / P_;
-      const uint32_t pi = (uint32_t)lw % P_, pc = (uint32_t)lw / P_;
-      const uint32_t j0 = g0 / P_, per_tile = nunits / P_;
-      for (uint32_t t = pc < nlp ? (pc + nlp - j0 % nlp) % nlp : per_tile; t < per_tile; t += nlp) {
-        const uint32_t u = pi + P_ * t, j = j0 + t;
-        const uint32_t stage = pi * nsp + j % nsp, phase = (j / nsp) & 1;
-        uint8_t *abase = sm + (size_t)stage * stage_bytes;
-        const uint32_t hdr = (u + p.nmma >= nunits) ? kHdrLast : 0u;  // the last unit of each issuer
-        if (u >= nreal) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          if (lane == 0) {
-            s_hdr[stage] = hdr;
-            s_smask[stage] = make_uint4(0u, 0u, 0u, 0u);
-            mbar_arrive(full_bar(stage));
-            mbar_arrive(full_bar(stage));
-          }
-          continue;
-        }
-        const int ak = (int)(u / KB), kb = (int)(u - ak * KB);
-        const int k = __fns(mask, 0, ak + 1);  // ak-th active offset
-        const int s0 = start[k], n = start[k + 1] - s0;
-        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + kb * kKB + chunk * 4);
-        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + kb * kKB + chunk * 4);
-        const float *srcc = p.src + kb * kKB + chunk * 4;
-        bool acquired = false;
-        auto acquire = [&]() {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          if (lane == 0) {
-            s_hdr[stage] = hdr;
-            s_smask[stage] = *reinterpret_cast<const uint4 *>(rec + 16 * k);
-            mbar_expect_tx(full_bar(stage), b_bytes);
-            bulk_g2s(smem_u32(abase + a_bytes), p.packed + (size_t)(k * KB + kb) * b_bytes, b_bytes, full_bar(stage));
-          }
-        };
-        for (int e0 = 0; e0 < n; e0 += 32) {
-          const int nq = min(8, (n - e0 + 3) >> 2);  // load instructions of this batch (warp-uniform)
+      const uint32_t rb = it % kNRec;
+      mbar_wait(recf_bar(rb), (it / kNRec) & 1);
+      const uint8_t *rec = s_rec + (size_t)rb * rec_buf;
+      const int nU = reinterpret_cast<const uint16_t *>(rec + 16 * p.K)[p.K + 1];
+      const int ng = min(nU, kRcap);
+      const int32_t *s_uidx = reinterpret_cast<const int32_t *>(rec + rec_stride);
+      for (int kb = 0; kb < KB; ++kb, ++q) {
+        const uint32_t slot = q % p.nrc;
+        mbar_wait(rce_bar(slot), ((q / p.nrc) & 1) ^ 1);
+        uint8_t *rcb = s_rc + (size_t)slot * rc_buf;
+        const int c0 = kb * kKB + chunk * 4;
+        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c0);
+        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c0);
+        for (int u0 = 0; u0 < ng; u0 += 128) {
           float4 v[8];
-          uint32_t slots[2] = {0, 0};
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q >= nq) break;
-            const int e = e0 + q * 4 + sub4;
-            if (e < n) {
-              const int32_t idx = ridx[s0 + e];
-              slots[q >> 2] |= (uint32_t)rslot[s0 + e] << (8 * (q & 3));
-              v[q] = __ldg(reinterpret_cast<const float4 *>(srcc + (int64_t)idx * p.Cin));
-            }
-          }
-          if (!acquired) {  // the first batch of loads is in flight while the stage drains
-            acquired = true;
-            acquire();
+          for (int i = 0; i < 8; ++i) {
+            const int u = u0 + i * 16 + rsub;
+            if (u < ng) v[i] = load_row4(p, s_uidx[u], c0);
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q >= nq) break;
-            const int e = e0 + q * 4 + sub4;
-            if (e < n) {
-              const uint32_t slot = (slots[q >> 2] >> (8 * (q & 3))) & 0xffu;
-              const uint32_t off = sw64(slot, c16) + sub;
-              const float4 x = v[q];
-              float4 y = make_float4(fmaf(x.x, sc.x, sh.x), fmaf(x.y, sc.y, sh.y), fmaf(x.z, sc.z, sh.z),
-                                     fmaf(x.w, sc.w, sh.w));
-              if (p.in_relu) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
-              uint2 hv = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
-              *reinterpret_cast<uint2 *>(abase + off) = hv;
+          for (int i = 0; i < 8; ++i) {
+            const int u = u0 + i * 16 + rsub;
+            if (u < ng) {
+              const float4 y = prologue4(v[i], sc, sh, p.in_relu);
               if (NS == 2) {
-                // bf16 -> fp32 is a 16-bit shift: the residual y - hi is exact in fp32
-                const float fx = __uint_as_float(hv.x << 16), fy = __uint_as_float(hv.x & 0xffff0000u);
-                const float fz = __uint_as_float(hv.y << 16), fw = __uint_as_float(hv.y & 0xffff0000u);
-                __nv_bfloat162 m0 = __floats2bfloat162_rn(y.x - fx, y.y - fy);
-                __nv_bfloat162 m1 = __floats2bfloat162_rn(y.z - fz, y.w - fw);
-                uint2 mv = make_uint2(*reinterpret_cast<uint32_t *>(&m0), *reinterpret_cast<uint32_t *>(&m1));
-                *reinterpret_cast<uint2 *>(abase + kABlockBytes + off) = mv;
+                // hi half and mid half of a row swap places on odd rows (bank spread); 16-byte chunk c of the
+                // logical row [hi 0..3 | mid 4..7] lives at chunk c ^ ((u & 1) << 2)
+                const uint32_t x4 = (uint32_t)(u & 1) << 2;
+                uint8_t *r = rcb + (size_t)u * row_b + (chunk & 1) * 8;
+                *reinterpret_cast<uint2 *>(r + (((chunk >> 1) ^ x4) << 4)) =
+                    make_uint2(split2(y.x, y.y, 0), split2(y.z, y.w, 0));
+                *reinterpret_cast<uint2 *>(r + ((((chunk >> 1) + 4) ^ x4) << 4)) =
+                    make_uint2(split2(y.x, y.y, 1), split2(y.z, y.w, 1));
+              } else {
+                *reinterpret_cast<uint2 *>(rcb + (size_t)u * row_b + chunk * 8) =
+                    make_uint2(split2(y.x, y.y, 0), split2(y.z, y.w, 0));
               }
             }
           }
         }
-        if (!acquired) acquire();  // a unit without entries (the tile has none at all)
-        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (lane == 0) mbar_arrive(rcf_bar(slot));
       }
-      g0 += nunits;
       __syncwarp();
       if (lane == 0) mbar_arrive(rece_bar(rb));  // this warp no longer reads s_rec[rb]
     }
-  } else if (warp < kEpiWarps + kLoadWarps + kMmaWarps) {
+  } else if (warp < kMmaWarp0) {
+    // ===================== builders: one WARP per pipeline unit, shared memory -> shared memory =====================
+    // Unit = (32-channel block kb, active kernel offset k) of a tile; the CTA's j-th unit lives in A stage j % na and
+    // is assembled by builder warp j % kBuildWarps: the entries of offset k copy their converted row from the row
+    // cache into the 64B-swizzled K-major block the UMMA descriptor expects, at the row of their tile slot.
+    const int b = warp - (kEpiWarps + kGatherWarps);
+    constexpr int LPE = 4 * NS;    // lanes per entry (16 bytes each: 4 hi chunks [+ 4 mid chunks])
+    constexpr int EPI = 32 / LPE;  // entries per warp instruction
+    const int e_in = lane / LPE, l = lane % LPE, part = l >> 2, c16 = l & 3;
+    const uint32_t s_a32 = smem_u32(s_a), s_rc32 = smem_u32(s_rc);
+    uint32_t it = 0, q = 0, j0 = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t rb = it % kNRec;
+      mbar_wait(recf_bar(rb), (it / kNRec) & 1);
+      const uint8_t *rec = s_rec + (size_t)rb * rec_buf;
+      const uint16_t *start = reinterpret_cast<const uint16_t *>(rec + 16 * p.K);
+      const int P = start[p.K];
+      const uint16_t *eloc = reinterpret_cast<const uint16_t *>(rec + hdr_bytes);
+      const uint8_t *eslot = rec + hdr_bytes + 2 * P;
+      // active offsets of the tile (those with at least one entry); a tile without any entry still sends one
+      // all-lanes-off unit through the pipeline so that its rows are written (zeros + residual)
+      uint32_t mask = __ballot_sync(0xffffffffu, lane < p.K && start[lane + 1] > start[lane]);
+      if (mask == 0) mask = 1u;
+      const uint32_t nact = (uint32_t)__popc(mask);
+      for (int kb = 0; kb < KB; ++kb, ++q) {
+        const uint32_t slot = q % p.nrc;
+        mbar_wait(rcf_bar(slot), (q / p.nrc) & 1);
+        const uint32_t rcb = s_rc32 + slot * rc_buf;
+        const uint32_t jb = j0 + (uint32_t)kb * nact;
+        for (uint32_t ak = ((uint32_t)b + kBuildWarps - jb % kBuildWarps) % kBuildWarps; ak < nact; ak += kBuildWarps) {
+          const uint32_t j = jb + ak;
+          const uint32_t stage = j & (na - 1), phase = (j >> p.lna) & 1;
+          const int k = __fns(mask, 0, ak + 1);  // ak-th active offset
+          const int s0 = start[k], n = start[k + 1] - s0;
+          mbar_wait(aempty_bar(stage), phase ^ 1);
+          if (lane == 0) s_smask[stage] = *reinterpret_cast<const uint4 *>(rec + 16 * k);
+          const uint32_t abase = s_a32 + stage * a_stage + (uint32_t)part * kABlockBytes;
+          for (int e0 = 0; e0 < n; e0 += 4 * EPI) {
+            uint4 v[4];
+            uint32_t off[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int e = e0 + i * EPI + e_in;
+              if (e < n) {
+                const uint32_t loc = eloc[s0 + e];
+                off[i] = sw64(eslot[s0 + e], c16);
+                if (loc < kRcap) {
+                  v[i] = lds128(rcb + loc * row_b + ((NS == 2 ? ((uint32_t)l ^ ((loc & 1u) << 2)) : (uint32_t)l) << 4));
+                } else {
+                  // the tile reads more distinct rows than a row-cache buffer holds: fetch this one directly
+                  const int32_t row = __ldg(p.uidx + tile * (int64_t)(kTileM * p.K) + loc);
+                  const int c0 = kb * kKB + c16 * 8;
+                  const float4 y0 = prologue4(load_row4(p, row, c0), *reinterpret_cast<const float4 *>(s_scale + c0),
+                                              *reinterpret_cast<const float4 *>(s_shift + c0), p.in_relu);
+                  const float4 y1 = prologue4(load_row4(p, row, c0 + 4), *reinterpret_cast<const float4 *>(s_scale + c0 + 4),
+                                              *reinterpret_cast<const float4 *>(s_shift + c0 + 4), p.in_relu);
+                  v[i] = make_uint4(split2(y0.x, y0.y, part), split2(y0.z, y0.w, part), split2(y1.x, y1.y, part),
+                                    split2(y1.z, y1.w, part));
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int e = e0 + i * EPI + e_in;
+              if (e < n) sts128(abase + off[i], v[i]);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(afull_bar(stage));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rce_bar(slot));  // this warp no longer reads row-cache buffer `slot`
+      }
+      j0 += nact * (uint32_t)KB;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rece_bar(rb));  // this warp no longer reads s_rec[rb]
+    }
+  } else if (warp < kMmaWarp0 + kMmaWarps) {
     // ===================== MMA issuers =====================
-    // Issuer i (one elected thread of warp 12+i) takes the units g = i (mod nmma) and accumulates into its own TMEM
-    // accumulators: M=128 x N=Cout x K=16 MMAs are short (N/2 cycles), so a single dependent accumulate chain issued
-    // by a single thread is bound by the MMA pipeline latency and the per-unit barrier handling, not by the tensor
-    // pipe.  Independent chains (nacc accumulators, summed by the epilogue) and two issuers hide both.
-    const int mi = warp - (kEpiWarps + kLoadWarps);
+    // Issuer i (one elected thread of warp kMmaWarp0 + i) takes the units j = i (mod nmma) and accumulates into its
+    // own TMEM accumulators: M=128 x N=Cout x K=16 MMAs are short (N/2 cycles), so a single dependent accumulate
+    // chain issued by a single thread is bound by the MMA pipeline latency and the per-unit barrier handling, not by
+    // the tensor pipe.  Independent chains (nacc accumulators, summed by the epilogue) and two issuers hide both.
+    const int mi = warp - kMmaWarp0;
     if (lane == 0 && mi < p.nmma) {
       const uint32_t idesc = make_idesc(p.Cout);
-      const uint32_t nsp = (uint32_t)(p.nstage / p.nmma);
-      const uint32_t sm_base = smem_u32(sm);
+      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
       const uint64_t desc0 = make_desc(0);
-      uint32_t j = 0;  // units this issuer has consumed
+      uint32_t j0 = 0;
       uint32_t as = 0, aph = 0;
       const uint32_t per = (uint32_t)(p.nacc / p.nmma);  // accumulators of this issuer: mi, mi + nmma, ...
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const uint32_t n = (uint32_t)__popc((uint32_t)__ldg(p.meta + tile).z) * (uint32_t)KB;
         mbar_wait(acce_bar(as), aph ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + as * (uint32_t)(p.nacc * p.Cout);
         const uint32_t d0 = d_base + mi * p.Cout, d1 = per > 1 ? d0 + p.nmma * p.Cout : d0;
-        while (true) {
-          const uint32_t stage = mi * nsp + j % nsp, phase = (j / nsp) & 1;
-          mbar_wait(full_bar(stage), phase);
+        for (uint32_t u = ((uint32_t)mi - j0) & (uint32_t)(p.nmma - 1); u < n; u += p.nmma) {
+          const uint32_t j = j0 + u;
+          const uint32_t sa = j & (na - 1), sw = j & (nw - 1);
+          mbar_wait(afull_bar(sa), (j >> p.lna) & 1);
+          mbar_wait(wfull_bar(sw), (j >> p.lnw) & 1);
           tc_fence_after();
-          const uint32_t hdr = *reinterpret_cast<volatile uint32_t *>(s_hdr + stage);
           uint4 vm;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                        : "=r"(vm.x), "=r"(vm.y), "=r"(vm.z), "=r"(vm.w)
-                       : "r"(smem_u32(s_smask + stage))
+                       : "r"(smem_u32(s_smask + sa))
                        : "memory");
           const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
-          const uint32_t a0 = sm_base + stage * stage_bytes;
-          const uint64_t ad = desc0 + (a0 >> 4), bd = desc0 + ((a0 + a_bytes) >> 4);
+          const uint64_t ad = desc0 + ((a_base + sa * a_stage) >> 4), bd = desc0 + ((w_base + sw * w_stage) >> 4);
           if ((vm.x | vm.y | vm.z | vm.w) != 0) {
             // accumulators of this issuer alternate between consecutive MMAs (independent chains)
             mma_bf16(d0, ad, bd, idesc, off);
@@ -434,10 +508,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
               mma_bf16(d1, ad + (kABlockBytes >> 4) + 2, bd + 2, idesc, off);
             }
           }
-          mma_commit(empty_bar(stage));
-          ++j;
-          if (hdr & kHdrLast) break;
+          mma_commit(aempty_bar(sa));
+          mma_commit(wempty_bar(sw));
         }
+        j0 += n;
         mma_commit(accf_bar(as));
         if (++as == 2) {
           as = 0;
@@ -446,16 +520,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       }
     }
     __syncwarp();
-  } else {
-    // ===================== record producer: 1-D bulk copy of each tile's record, nrec-1 tiles ahead ===============
+  } else if (warp == kMmaWarp0 + kMmaWarps) {
+    // ===================== record producer: bulk copies of each tile's record, kNRec - 1 tiles ahead ===============
     if (lane == 0) {
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t rb = it % p.nrec;
-        const uint32_t bytes = (uint32_t)__ldg(p.rec_bytes + tile);
-        mbar_wait(rece_bar(rb), ((it / p.nrec) & 1) ^ 1);
-        mbar_expect_tx(recf_bar(rb), bytes);
-        bulk_g2s(smem_u32(s_rec + (size_t)rb * rec_stride), p.recs + tile * (int64_t)rec_stride, bytes, recf_bar(rb));
+        const uint32_t rb = it % kNRec;
+        const int4 m = __ldg(p.meta + tile);
+        const uint32_t ub = ((uint32_t)min(m.y, kRcap) * 4u + 15u) & ~15u;
+        mbar_wait(rece_bar(rb), ((it / kNRec) & 1) ^ 1);
+        mbar_expect_tx(recf_bar(rb), (uint32_t)m.x + ub);
+        const uint32_t dst = smem_u32(s_rec + (size_t)rb * rec_buf);
+        bulk_g2s(dst, p.recs + tile * (int64_t)rec_stride, (uint32_t)m.x, recf_bar(rb));
+        if (ub) bulk_g2s(dst + rec_stride, p.uidx + tile * (int64_t)(kTileM * p.K), ub, recf_bar(rb));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== weight producer: bulk copy of each unit's pre-swizzled weight block, nw units ahead =====
+    if (lane == 0) {
+      uint32_t j = 0;
+      const uint32_t w_base = smem_u32(s_w);
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const uint32_t mask = (uint32_t)__ldg(p.meta + tile).z;
+        for (int kb = 0; kb < KB; ++kb) {
+          for (uint32_t mm = mask; mm; mm &= mm - 1, ++j) {
+            const int k = __ffs(mm) - 1;
+            const uint32_t sw = j & (nw - 1);
+            mbar_wait(wempty_bar(sw), ((j >> p.lnw) & 1) ^ 1);
+            mbar_expect_tx(wfull_bar(sw), w_stage);
+            bulk_g2s(w_base + sw * w_stage, p.packed + (size_t)(k * KB + kb) * w_stage, w_stage, wfull_bar(sw));
+          }
+        }
       }
     }
     __syncwarp();
@@ -463,16 +559,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kEpiWarps + kLoadWarps) {
+  if (warp == kMmaWarp0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
   }
 }
 
-// W[K, Cin_w, Cout_w] fp32 -> [K][KB][NS][N x 64 B swizzled] bf16 (hi, mid)
+// W[K, Cin_w, Cout_w] fp32 -> [K][KB][NS][N x 64 B swizzled] bf16 (hi, mid); KB = ceil(Cin / 32), the channels
+// beyond Cin are zero
 __global__ void pack_weights_kernel(const float *__restrict__ W, int K, int Cin, int Cout, int transpose_w, int NS,
                                     uint8_t *__restrict__ packed) {
-  const int KB = Cin / kKB;
+  const int KB = (Cin + kKB - 1) / kKB;
   const int64_t total = (int64_t)K * KB * Cout * kKB;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int kk = (int)(e % kKB);
@@ -480,7 +577,7 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int K, int Cin,
     int kb = (int)((e / ((int64_t)kKB * Cout)) % KB);
     int k = (int)(e / ((int64_t)kKB * Cout * KB));
     int c = kb * kKB + kk;
-    float w = transpose_w ? W[((int64_t)k * Cout + n) * Cin + c] : W[((int64_t)k * Cin + c) * Cout + n];
+    float w = c >= Cin ? 0.f : transpose_w ? W[((int64_t)k * Cout + n) * Cin + c] : W[((int64_t)k * Cin + c) * Cout + n];
     __nv_bfloat16 hi = __float2bfloat16_rn(w);
     size_t block = ((size_t)k * KB + kb) * NS * (size_t)Cout * 64;
     uint32_t off = sw64((uint32_t)n, (uint32_t)(kk >> 3)) + (kk & 7) * 2;
@@ -501,12 +598,12 @@ using namespace wsis::umma;
 extern "C" {
 
 int wsis_conv_umma_supported(int Cin, int Cout) {
-  return Cin >= 32 && Cin % 32 == 0 && Cout >= 16 && Cout % 16 == 0 && Cout <= 256;
+  return Cin >= 1 && Cin <= 1024 && Cout >= 16 && Cout % 16 == 0 && Cout <= 256;
 }
 
 int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision) {
   int NS = precision == 3 ? 2 : 1;
-  return (int64_t)K * (Cin / kKB) * NS * Cout * 64;
+  return (int64_t)K * ((Cin + kKB - 1) / kKB) * NS * Cout * 64;
 }
 
 int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
@@ -514,7 +611,7 @@ int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpo
   WSIS_CHECK(wsis_conv_umma_supported(Cin, Cout), "pack_weights: unsupported Cin=%d Cout=%d", Cin, Cout);
   WSIS_CHECK(precision == 1 || precision == 3, "pack_weights: precision must be 1 or 3");
   WSIS_CHECK((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "pack_weights: packed must be 16-byte aligned");
-  int64_t total = (int64_t)K * Cin * Cout;
+  int64_t total = (int64_t)K * ((Cin + kKB - 1) / kKB) * kKB * Cout;
   unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8);
   pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(W, K, Cin, Cout, transpose_w, precision == 3 ? 2 : 1,
                                                              (uint8_t *)packed);
@@ -522,24 +619,25 @@ int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpo
   return 0;
 }
 
-int wsis_conv_umma(const float *src, const void *records, const int32_t *rec_bytes, const int32_t *order,
-                   int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
+int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, const int32_t *meta,
+                   const int32_t *order, int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
                    const float *in_scale, const float *in_shift, int in_relu, const float *residual, float *dst,
                    wsis_stream_t stream) {
   WSIS_CHECK(wsis_conv_umma_supported(Cin, Cout), "conv_umma: unsupported Cin=%d Cout=%d", Cin, Cout);
   WSIS_CHECK(K >= 1 && K <= 32, "conv_umma: kernel volume %d not in [1,32]", K);
   WSIS_CHECK(precision == 1 || precision == 3, "conv_umma: precision must be 1 or 3");
   WSIS_CHECK((in_scale == nullptr) == (in_shift == nullptr), "conv_umma: in_scale/in_shift must both be set");
-  WSIS_CHECK(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
-               reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(packed) |
-               reinterpret_cast<uintptr_t>(records)) & 15) == 0,
-             "conv_umma: src/dst/residual/packed/records must be 16-byte aligned");
+  WSIS_CHECK(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(residual) |
+               reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(records) |
+               reinterpret_cast<uintptr_t>(uidx) | reinterpret_cast<uintptr_t>(meta)) & 15) == 0,
+             "conv_umma: dst/residual/packed/records/uidx/meta must be 16-byte aligned");
   if (num_tiles == 0) return 0;
   const int NS = precision == 3 ? 2 : 1;
   Params p;
   p.src = src;
   p.recs = (const uint8_t *)records;
-  p.rec_bytes = rec_bytes;
+  p.uidx = uidx;
+  p.meta = reinterpret_cast<const int4 *>(meta);
   p.order = order;
   p.packed = (const uint8_t *)packed;
   p.in_scale = in_scale;
@@ -549,7 +647,9 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *rec_byt
   p.K = K;
   p.Cin = Cin;
   p.Cout = Cout;
+  p.KB = (Cin + kKB - 1) / kKB;
   p.in_relu = in_relu;
+  p.vec4 = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   p.num_tiles = num_tiles;
   // independent accumulate chains per accumulator buffer: as many as the 512 TMEM columns allow, up to 4
   int nacc = 4;
@@ -559,22 +659,27 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *rec_byt
   int cols = 32;
   while (cols < 2 * nacc * Cout) cols <<= 1;
   p.tmem_cols = cols;
-  const int64_t stage_bytes = (int64_t)NS * kABlockBytes + (int64_t)NS * Cout * 64;
-  const int64_t rec_stride = rec_stride_bytes(K);
-  const int64_t misc = 1024 /*align*/ + 2 * Cin * 4 + 16 * 16 + 16 * 4 + (2 * 16 + 4 + 2 * 3) * 8 + 64;
+  // shared memory: A ring (2^lna stages), weight ring (2^lnw), row cache (nrc buffers), records; shrink the rings
+  // in this order of preference until the layer fits
+  const int64_t a_stage = (int64_t)NS * kABlockBytes, w_stage = (int64_t)NS * Cout * 64;
+  const int64_t rc_buf = (int64_t)kRcap * NS * 64, rec_buf = rec_stride_bytes(K) + kRcap * 4;
+  static const int pref[][3] = {{2, 3, 3}, {2, 2, 3}, {2, 3, 2}, {2, 2, 2}, {1, 2, 2}, {1, 1, 2}, {1, 1, 1}};
   const int64_t budget = 226 * 1024;
-  // three record buffers keep the record copies two tiles ahead; fall back to two when the stages need the room
-  int nrec = 3;
-  int nstage = (int)std::min<int64_t>(16, (budget - misc - nrec * rec_stride) / stage_bytes);
-  if (nstage < kLoadWarps) {
-    nrec = 2;
-    nstage = (int)std::min<int64_t>(16, (budget - misc - nrec * rec_stride) / stage_bytes);
+  int64_t smem = 0;
+  bool fit = false;
+  for (auto &c : pref) {
+    const int na = 1 << c[0], nw = 1 << c[1], nrc = c[2];
+    const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nw + 2 * nrc + 2 * kNRec + 4) * 8 + 64;
+    smem = misc + na * a_stage + nw * w_stage + nrc * rc_buf + kNRec * rec_buf;
+    if (smem <= budget) {
+      p.lna = c[0];
+      p.lnw = c[1];
+      p.nrc = nrc;
+      fit = true;
+      break;
+    }
   }
-  WSIS_CHECK(nstage >= 2, "conv_umma: shared memory budget exceeded for Cin=%d Cout=%d K=%d", Cin, Cout, K);
-  p.nstage = nstage / p.nmma * p.nmma;
-  p.nrec = nrec;
-  p.nlw = std::min(kLoadWarps / p.nmma, p.nstage / p.nmma);  // loader warps per pipeline
-  const int64_t smem = misc + nrec * rec_stride + nstage * stage_bytes;
+  WSIS_CHECK(fit, "conv_umma: shared memory budget exceeded for Cin=%d Cout=%d K=%d", Cin, Cout, K);
   auto kern = NS == 2 ? conv_umma_kernel<2> : conv_umma_kernel<1>;
   static int64_t smem_set[2] = {0, 0};
   if (smem > smem_set[NS - 1]) {

@@ -42,36 +42,55 @@ __global__ void iota_kernel(int32_t *order, int64_t N, int64_t n_pad) {
 
 // ------------------------------------------------------------------------------------------------
 // Tile records: what one conv CTA needs to know about one tile of 128 destination rows, compacted.
-//   [0, 16K)                 valid[K][4]  u32   bit r of valid[k] = tile slot r has a source row through offset k
-//   [16K, 16K + hdr2)        start[K+1]   u16   entries of offset k are [start[k], start[k+1])
-//   [hdr, hdr + 4P)          idx[P]       i32   source row of each entry (P = start[K] <= 128K)
-//   [hdr + 4P, hdr + 5P)     slot[P]      u8    tile slot (accumulator lane) of each entry, ascending inside an offset
-// Records live at a fixed stride (worst case P = 128K) so they are built in one pass without a size scan; a CTA
-// copies only rec_bytes[t] = align16(hdr + 5P) of it.  On a surface sampled like a scan P is ~4-10 per row instead
-// of K = 27, so the map traffic of a layer drops from 108 B to ~25-50 B per row and absent (row, offset) slots cost
-// the conv kernel nothing.
+//   entry record (records + t * rec_stride_bytes(K), meta[t].x bytes of it are meaningful)
+//     [0, 16K)              valid[K][4]  u32   bit r of valid[k] = tile slot r has a source row through offset k
+//     [16K, hdr)            start[K+1]   u16   entries of offset k are [start[k], start[k+1]);  then nU u16
+//     [hdr, hdr + 2P)       eloc[P]      u16   index of the entry's source row in the tile's UNIQUE-row list
+//     [hdr + 2P, hdr + 3P)  eslot[P]     u8    tile slot (accumulator lane) of the entry, ascending inside an offset
+//   unique rows (uidx + t * 128K)  i32[nU]     the distinct source rows the tile reads; a surface patch of 128
+//                                              voxels reads ~160-230 distinct rows through ~480-1400 entries, so the
+//                                              conv kernel fetches (and converts) every source row ONCE per tile
+//   meta[t] = {entry-record bytes, nU, active-offset mask (1 if the tile has no entry at all), P}
+// Records live at a fixed stride (worst case P = 128K) so they are built in one pass without a size scan.
 // ------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__restrict__ map, int K, int flip,
+__device__ __forceinline__ uint32_t tile_hash(int32_t v, uint32_t mask) {
+  return ((uint32_t)v ^ ((uint32_t)v >> 13)) & mask;  // keeps runs of consecutive rows in order
+}
+
+__global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__restrict__ map, int K, int flip, int HT,
                                                             const int32_t *__restrict__ order, uint8_t *__restrict__ recs,
-                                                            int32_t *__restrict__ rec_bytes) {
-  extern __shared__ int32_t s_map[];  // [K][128] transposed slice, then the K+1 prefix
-  int32_t *s_cnt = s_map + K * kTile;
+                                                            int32_t *__restrict__ uidx, int4 *__restrict__ meta) {
+  extern __shared__ int32_t s_map[];  // [K][128] transposed slice
+  int32_t *s_cnt = s_map + K * kTile;                                   // [4K + 1] entry prefix, [4] table prefix
+  int32_t *s_tab = s_cnt + 4 * K + 8;                                   // [HT] open-addressing set of source rows
+  uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_tab + HT);           // [K][128] table slot of each entry
   const int64_t t = blockIdx.x;
   const int r = threadIdx.x, lane = r & 31, w = r >> 5;
   const int32_t dst = __ldg(order + t * kTile + r);
   for (int k = 0; k < K; ++k)
     s_map[k * kTile + r] = dst >= 0 ? __ldg(map + (int64_t)dst * K + (flip ? K - 1 - k : k)) : -1;
+  for (int i = r; i < HT; i += kTile) s_tab[i] = -1;
   __syncthreads();
   uint8_t *rec = recs + t * (int64_t)rec_stride_bytes(K);
   uint32_t *valid = reinterpret_cast<uint32_t *>(rec);
   uint16_t *start = reinterpret_cast<uint16_t *>(rec + 16 * K);
-  // per-offset population (one warp ballot per 32 slots)
+  // per-offset population (one warp ballot per 32 slots) and insertion of the source rows into the set
   for (int k = 0; k < K; ++k) {
-    const uint32_t bal = __ballot_sync(0xffffffffu, s_map[k * kTile + r] >= 0);
+    const int32_t v = s_map[k * kTile + r];
+    const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
     if (lane == 0) {
       valid[k * 4 + w] = bal;
       s_cnt[k * 4 + w] = __popc(bal);
+    }
+    if (v >= 0) {
+      uint32_t h = tile_hash(v, HT - 1);
+      while (true) {
+        const int32_t prev = atomicCAS(s_tab + h, -1, v);
+        if (prev == -1 || prev == v) break;
+        h = (h + 1) & (HT - 1);
+      }
+      s_pos[k * kTile + r] = (uint16_t)h;
     }
   }
   __syncthreads();
@@ -84,21 +103,48 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
     }
     s_cnt[K * 4] = run;
   }
+  // compaction of the set: warp w owns table quarter w; pass 1 counts, pass 2 ranks (table slot -> unique index)
+  const int q0 = w * (HT / 4), q1 = q0 + HT / 4;
+  int cnt = 0;
+  for (int i = q0 + lane; i < q1; i += 32) cnt += __popc(__ballot_sync(0xffffffffu, s_tab[i] >= 0)) * (lane == 0);
+  if (lane == 0) s_cnt[4 * K + 1 + w] = cnt;
+  __syncthreads();
+  int base = 0;
+  for (int i = 0; i < w; ++i) base += s_cnt[4 * K + 1 + i];
+  const int nU = s_cnt[4 * K + 1] + s_cnt[4 * K + 2] + s_cnt[4 * K + 3] + s_cnt[4 * K + 4];
+  int32_t *u = uidx + t * (int64_t)(kTile * K);
+  for (int i = q0 + lane; i < q1; i += 32) {
+    const int32_t v = s_tab[i];
+    const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
+    if (v >= 0) {
+      const int rank = base + __popc(bal & ((1u << lane) - 1u));
+      u[rank] = v;
+      s_tab[i] = rank;
+    }
+    base += __popc(bal);
+  }
   __syncthreads();
   const int P = s_cnt[K * 4];
   if (r <= K) start[r] = (uint16_t)(r < K ? s_cnt[r * 4] : P);
-  int32_t *idx = reinterpret_cast<int32_t *>(rec + rec_hdr_bytes(K));
-  uint8_t *slot = rec + rec_hdr_bytes(K) + 4 * P;
+  if (r == 0) start[K + 1] = (uint16_t)nU;
+  uint16_t *eloc = reinterpret_cast<uint16_t *>(rec + rec_hdr_bytes(K));
+  uint8_t *eslot = rec + rec_hdr_bytes(K) + 2 * P;
   for (int k = 0; k < K; ++k) {
     const int32_t v = s_map[k * kTile + r];
     const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
     if (v >= 0) {
       const int pos = s_cnt[k * 4 + w] + __popc(bal & ((1u << lane) - 1u));
-      idx[pos] = v;
-      slot[pos] = (uint8_t)r;
+      eloc[pos] = (uint16_t)s_tab[s_pos[k * kTile + r]];
+      eslot[pos] = (uint8_t)r;
     }
   }
-  if (r == 0) rec_bytes[t] = (rec_hdr_bytes(K) + 5 * P + 15) & ~15;
+  // amask: offsets with an entry anywhere in the tile (s_cnt holds the prefix, so compare neighbours)
+  if (r == 0) {
+    uint32_t am = 0;
+    for (int k = 0; k < K; ++k)
+      if (s_cnt[(k + 1) * 4] > s_cnt[k * 4]) am |= 1u << k;
+    meta[t] = make_int4((rec_hdr_bytes(K) + 3 * P + 15) & ~15, nU, (int)(am ? am : 1u), P);
+  }
 }
 
 static int ilog2_ceil(int64_t v) {
@@ -161,15 +207,31 @@ int wsis_identity_order(int64_t N, int32_t *order, wsis_stream_t stream) {
 
 int64_t wsis_tile_record_stride(int K) { return rec_stride_bytes(K); }
 
+int64_t wsis_tile_unique_stride(int K) { return (int64_t)kTile * K; }
+
+static int tile_table_slots(int K) {
+  int ht = 256;
+  while (ht < 2 * kTile * K) ht <<= 1;
+  return ht;
+}
+
 int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const int32_t *order, void *records,
-                      int32_t *rec_bytes, wsis_stream_t stream) {
+                      int32_t *uidx, int32_t *meta, wsis_stream_t stream) {
   const int64_t n_tiles = wsis_tile_pad(n_rows) / kTile;
   if (n_tiles == 0) return 0;
   WSIS_CHECK(K >= 1 && K <= 32, "tile_records: kernel volume %d not in [1,32]", K);
-  WSIS_CHECK((reinterpret_cast<uintptr_t>(records) & 15) == 0, "tile_records: records must be 16-byte aligned");
-  size_t smem = ((size_t)K * kTile + 4 * K + 1) * sizeof(int32_t);
-  tile_record_kernel<<<(unsigned)n_tiles, kTile, smem, as_stream(stream)>>>(map, K, flip, order, (uint8_t *)records,
-                                                                             rec_bytes);
+  WSIS_CHECK(((reinterpret_cast<uintptr_t>(records) | reinterpret_cast<uintptr_t>(uidx) |
+               reinterpret_cast<uintptr_t>(meta)) & 15) == 0,
+             "tile_records: records/uidx/meta must be 16-byte aligned");
+  const int HT = tile_table_slots(K);
+  size_t smem = ((size_t)K * kTile + 4 * K + 8 + HT) * sizeof(int32_t) + (size_t)K * kTile * sizeof(uint16_t);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    WSIS_CUDA(cudaFuncSetAttribute(tile_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  tile_record_kernel<<<(unsigned)n_tiles, kTile, smem, as_stream(stream)>>>(
+      map, K, flip, HT, order, (uint8_t *)records, uidx, reinterpret_cast<int4 *>(meta));
   WSIS_LAUNCH_OK();
   return 0;
 }

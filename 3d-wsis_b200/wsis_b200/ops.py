@@ -107,12 +107,14 @@ class TileMap:
         self.order = order
         self.num_tiles = lib().value("wsis_tile_pad", n_dst) // 128
         self.stride = lib().value("wsis_tile_record_stride", K)
-        # fixed-stride records (only rec_bytes[t] of each are ever read): no size scan, no host sync
+        self.ustride = lib().value("wsis_tile_unique_stride", K)
+        # fixed-stride records (only the meaningful head of each is ever written or read): no size scan, no host sync
         self.records = _bytes(self.num_tiles * self.stride, map_.device)
-        self.rec_bytes = torch.empty((max(self.num_tiles, 1),), dtype=torch.int32, device=map_.device)
+        self.uidx = torch.empty((max(self.num_tiles * self.ustride, 4),), dtype=torch.int32, device=map_.device)
+        self.meta = torch.empty((max(self.num_tiles, 1), 4), dtype=torch.int32, device=map_.device)
         if n_dst > 0:
             lib().call("wsis_tile_records", _ptr(map_), n_dst, K, int(flip), _ptr(order), _ptr(self.records),
-                       _ptr(self.rec_bytes), _stream())
+                       _ptr(self.uidx), _ptr(self.meta), _stream())
 
 
 def _tiles_of(map_, n_dst, flip):
@@ -338,7 +340,7 @@ def sparse_conv(src, weight3, map_, n_dst, flip, transpose_w=False, prologue=Non
         buf = packed.get(weight3, bool(transpose_w), prec)
         tiles = tiles if tiles is not None else _tiles_of(map_, n_dst, int(flip))
         assert tiles.n_dst == n_dst and tiles.K == K
-        lib().call("wsis_conv_umma", _ptr(src), _ptr(tiles.records), _ptr(tiles.rec_bytes), _ptr(tiles.order),
+        lib().call("wsis_conv_umma", _ptr(src), _ptr(tiles.records), _ptr(tiles.uidx), _ptr(tiles.meta), _ptr(tiles.order),
                    tiles.num_tiles, K, _ptr(buf), Cin, Cout, prec, _ptr(scale), _ptr(shift), int(relu), _ptr(residual),
                    _ptr(dst), _stream())
     else:

@@ -109,8 +109,8 @@ int wsis_nbr_from_pairs(const int32_t *pairs, const int32_t *num, int64_t pair_s
  * Pass NULL to disable either.  W is the reference layout [K, Cin_w, Cout_w] (conv.py:98-99);
  * transpose_w = 1 contracts with W[k]^T (dgrad), i.e. Cin = Cout_w and Cout = Cin_w. */
 
-/* exact-fp32 SIMT path (any Cin/Cout; used for the 6->32 input conv, odd widths and as the GPU-side
- * cross-check of the tensor-core path) */
+/* exact-fp32 SIMT path (any Cin/Cout; used for widths the tensor-core kernel does not take, for
+ * precision="simt" and as the GPU-side cross-check of the tensor-core path) */
 int wsis_conv_simt(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const float *W,
                    int transpose_w, int Cin, int Cout, const float *in_scale, const float *in_shift, int in_relu,
                    const float *residual, float *dst, wsis_stream_t stream);
@@ -121,27 +121,34 @@ int wsis_conv_simt(const float *src, const int32_t *map, int64_t n_dst, int K, i
  * wsis_identity_order gives the trivial order for callers without coordinates.
  * wsis_tile_records compacts a neighbour map into per-tile RECORDS, the only form of the rulebook the tensor-core
  * kernel reads: for tile t (destination rows order[128t .. 128t+127]) and `m[r,k] = map[order[..], flip ? K-1-k : k]`
- *   valid[K][4] u32 | start[K+1] u16 | idx[P] i32 (source rows) | slot[P] u8 (tile slots), P = pairs of the tile,
- * at a fixed stride wsis_tile_record_stride(K) (worst case P = 128 K), of which rec_bytes[t] bytes are meaningful.
- * records: uint8[num_tiles * stride] (16-byte aligned), rec_bytes: int32[num_tiles].  K <= 32. */
+ *   records + t * wsis_tile_record_stride(K):
+ *     valid[K][4] u32 | start[K+1] u16, nU u16 | eloc[P] u16 | eslot[P] u8          (P = pairs of the tile <= 128 K)
+ *     entries of offset k are [start[k], start[k+1]); eloc = index of the entry's source row in the tile's list of
+ *     DISTINCT source rows, eslot = tile slot (ascending inside an offset); valid[k] = slots that have an entry
+ *   uidx + t * wsis_tile_unique_stride(K): int32[nU] the distinct source rows of the tile (any order)
+ *   meta[t] = int32[4] {meaningful record bytes, nU, mask of offsets with an entry (1 if none at all), P}
+ * records: uint8[num_tiles * stride], uidx: int32[num_tiles * unique_stride], meta: int32[num_tiles * 4], all 16-byte
+ * aligned.  K <= 32. */
 int64_t wsis_tile_pad(int64_t n);
 int64_t wsis_spatial_order_ws_bytes(int64_t N);
 int wsis_spatial_order(const int32_t *coords, int64_t N, const int32_t spatial_shape[3], int batch_size,
                        int32_t *order, void *ws, wsis_stream_t stream);
 int wsis_identity_order(int64_t N, int32_t *order, wsis_stream_t stream);
 int64_t wsis_tile_record_stride(int K);
+int64_t wsis_tile_unique_stride(int K);
 int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const int32_t *order, void *records,
-                      int32_t *rec_bytes, wsis_stream_t stream);
+                      int32_t *uidx, int32_t *meta, wsis_stream_t stream);
 
 /* tcgen05 tensor-core path over tile records (num_tiles = wsis_tile_pad(n_dst)/128).  precision: 1 = bf16 operands
  * (1e-2 contract), 3 = bf16x3 split operands with fp32 accumulation in TMEM (1e-4 contract).
- * Requires Cin % 32 == 0, Cout % 16 == 0, 16 <= Cout <= 256, K <= 32. */
+ * Requires Cout % 16 == 0, 16 <= Cout <= 256, K <= 32; any Cin (channels are zero-padded to a multiple of 32 inside
+ * the kernel and in the packed weights; rows are read with 16-byte loads when Cin % 4 == 0 and src is aligned). */
 int wsis_conv_umma_supported(int Cin, int Cout);
 int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision);
 int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
                            wsis_stream_t stream);
-int wsis_conv_umma(const float *src, const void *records, const int32_t *rec_bytes, const int32_t *order,
-                   int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
+int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, const int32_t *meta,
+                   const int32_t *order, int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
                    const float *in_scale, const float *in_shift, int in_relu, const float *residual, float *dst,
                    wsis_stream_t stream);
 

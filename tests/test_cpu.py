@@ -264,7 +264,8 @@ def test_cabi_library_exports_every_declared_symbol():
     assert L.value("wsis_version") >= 100
     assert L.value("wsis_hash_slots", 1000) == 2048 and L.value("wsis_hash_slots", 1) == 1024
     assert L.value("wsis_tile_pad", 0) == 0 and L.value("wsis_tile_pad", 129) == 256
-    assert L.value("wsis_conv_umma_supported", 32, 32) == 1 and L.value("wsis_conv_umma_supported", 6, 32) == 0
+    assert L.value("wsis_conv_umma_supported", 32, 32) == 1 and L.value("wsis_conv_umma_supported", 6, 32) == 1
+    assert L.value("wsis_conv_umma_supported", 32, 24) == 0 and L.value("wsis_conv_pack_bytes", 27, 6, 32, 1) == 27 * 32 * 64
     assert L.value("wsis_conv_pack_bytes", 27, 64, 32, 3) == 27 * 2 * 2 * 32 * 64
     assert L.value("wsis_scan_ws_bytes", 1 << 20) > 0 and L.value("wsis_sort_ws_bytes", 1 << 20) > 0
     nm = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True).stdout

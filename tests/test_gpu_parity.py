@@ -531,24 +531,30 @@ def test_spatial_order_is_a_local_permutation(W, n, bs, shape):
 def _decode_records(t, K):
     """Tile records (include/wsis_b200.h: wsis_tile_records) -> dense int32[n_pad, K] map, checking the layout."""
     rec = t.records.cpu().numpy()
-    nbytes = t.rec_bytes.cpu().numpy()
-    hdr = 16 * K + ((2 * (K + 1) + 15) // 16) * 16
+    meta = t.meta.cpu().numpy()
+    uidx = t.uidx.cpu().numpy()
+    hdr = 16 * K + ((2 * (K + 2) + 15) // 16) * 16
     out = np.full((t.num_tiles * 128, K), -1, np.int32)
     for ti in range(t.num_tiles):
         r = rec[ti * t.stride:(ti + 1) * t.stride]
         valid = r[:16 * K].view(np.uint32).reshape(K, 4)
-        start = r[16 * K:16 * K + 2 * (K + 1)].view(np.uint16).astype(np.int64)
-        P = int(start[K])
-        assert nbytes[ti] == (hdr + 5 * P + 15) // 16 * 16 and start[0] == 0 and np.all(np.diff(start) >= 0)
-        idx = r[hdr:hdr + 4 * P].view(np.int32)
-        slot = r[hdr + 4 * P:hdr + 5 * P]
+        start = r[16 * K:16 * K + 2 * (K + 2)].view(np.uint16).astype(np.int64)
+        P, nU = int(start[K]), int(start[K + 1])
+        amask = sum(1 << k for k in range(K) if start[k + 1] > start[k]) or 1
+        assert list(meta[ti]) == [(hdr + 3 * P + 15) // 16 * 16, nU, amask, P]
+        assert start[0] == 0 and np.all(np.diff(start[:K + 1]) >= 0)
+        uniq = uidx[ti * t.ustride:ti * t.ustride + nU]
+        assert len(np.unique(uniq)) == nU                      # the tile's source rows, each exactly once
+        loc = r[hdr:hdr + 2 * P].view(np.uint16).astype(np.int64)
+        slot = r[hdr + 2 * P:hdr + 3 * P]
+        assert P == 0 or (loc.max() < nU and len(np.unique(loc)) == nU)
         for k in range(K):
             sl = slot[start[k]:start[k + 1]].astype(np.int64)
             assert np.all(np.diff(sl) > 0)
             bits = np.zeros(128, bool)
             bits[sl] = True
             assert np.array_equal(np.unpackbits(valid[k].view(np.uint8), bitorder="little").astype(bool), bits)
-            out[ti * 128 + sl, k] = idx[start[k]:start[k + 1]]
+            out[ti * 128 + sl, k] = uniq[loc[start[k]:start[k + 1]]]
     return out
 
 
@@ -627,3 +633,27 @@ def test_conv_tile_without_any_neighbour(W):
     exp[128:256] += f[128:256] @ w[13]
     assert rel(out, exp) < FP32_TOL
     assert np.array_equal(out[:128], res[:128]) and np.array_equal(out[256:], res[256:])
+
+
+@pytest.mark.parametrize("cin,cout", [(6, 32), (32, 32), (64, 48), (100, 16)])
+@pytest.mark.parametrize("prec,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_conv_row_cache_overflow_and_narrow_rows(W, cin, cout, prec, tol):
+    """Tiles that read far more distinct source rows than a row-cache buffer holds (a random map: up to 128*K distinct
+    rows per tile) take the direct-fetch path for the overflow; widths that are not a multiple of 32 (or of 4) are
+    zero-padded inside the kernel.  Checked against a direct numpy evaluation of the definition."""
+    rng = np.random.default_rng(cin * 1000 + cout)
+    n, K = 700, 27
+    m = rng.integers(0, n, (n, K)).astype(np.int32)
+    m[rng.random((n, K)) < 0.35] = -1
+    m[256:384] = rng.integers(0, n, (128, K))                  # a full tile: 3456 entries
+    f = rng.uniform(-1, 1, (n, cin)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (K, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cin).astype(np.float32)
+    shift = rng.uniform(-0.3, 0.3, cin).astype(np.float32)
+    g = np.maximum(f * scale + shift, 0).astype(np.float64)
+    exp = np.zeros((n, cout))
+    for k in range(K):
+        ok = m[:, k] >= 0
+        exp[ok] += g[m[ok, k]] @ w[k].astype(np.float64)
+    out = W.sparse_conv(cu(f), cu(w), cu(m), n, 0, prologue=(cu(scale), cu(shift), 1), precision=prec).cpu().numpy()
+    assert rel(out, exp) < tol
