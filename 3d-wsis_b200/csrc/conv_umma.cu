@@ -40,9 +40,9 @@ namespace umma {
 constexpr int kTileM = 128;
 constexpr int kKB = 32;                    // channels per pipeline unit (64 bytes of bf16 = one swizzle-64 row)
 constexpr int kABlockBytes = kTileM * 64;  // 8 KB
-constexpr int kEpiWarps = 4, kGatherWarps = 4, kBuildWarps = 6, kMmaWarps = 2, kProdWarps = 2;
-constexpr int kThreads = (kEpiWarps + kGatherWarps + kBuildWarps + kMmaWarps + kProdWarps) * 32;  // 576
-constexpr int kNRec = 2;    // tile records in flight
+constexpr int kEpiWarps = 4, kGatherWarps = 4, kBuildWarps = 4, kMmaWarps = 2, kProdWarps = 2;
+constexpr int kThreads = (kEpiWarps + kGatherWarps + kBuildWarps + kMmaWarps + kProdWarps) * 32;  // 512
+constexpr int kMaxRec = 4;  // tile records in flight (p.nrec <= kMaxRec)
 constexpr int kRcap = 256;  // rows of one row-cache buffer (a surface tile reads ~160-230 distinct rows)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -56,22 +56,70 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// try_wait suspends the thread in hardware until the phase completes or the time hint expires, so waiting
-// warps do not burn issue slots the loader warps need
+// Diagnostics (timing experiments through WSIS_CONV_DEBUG and the CTA-0 timeline) are compiled in only with
+// -DWSIS_CONV_DIAG=1: in the product build they cost nothing on the single-warp critical paths.
+#ifndef WSIS_CONV_DIAG
+#define WSIS_CONV_DIAG 0
+#endif
+constexpr bool kDiag = WSIS_CONV_DIAG != 0;
+#define WSIS_DBG(bit) (kDiag && (p.dbg & (bit)))
+
+// try_wait blocks in hardware for a short, implementation-defined time; NO suspend-time hint: with a hint ptxas emits
+// NANOSLEEP.SYNCS after a failed probe and the wake-up latency of a sleeping warp (on both sides of every stage hand-off)
+// dominated the pipeline's round trip.  A wait that has not completed after ~4 s is a protocol bug: report which
+// barrier and trap instead of hanging the device.
+__device__ __noinline__ void mbar_deadlock(uint32_t bar, uint32_t parity) {
+  printf("wsis conv_umma: barrier wait timed out: block %d warp %d lane %d barrier@%u parity %u\n", (int)blockIdx.x,
+         (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
+  uint32_t ok, fails = 0;
   do {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "r"(bar), "r"(parity)
         : "memory");
+    // every failed try_wait has already blocked for a hardware time quantum: 2^22 of them in a row is seconds
+    if (!ok && ++fails == (1u << 22)) mbar_deadlock(bar, parity);
   } while (!ok);
 }
+
+// One lane of a fully active warp.  Code under this predicate is known to be single-lane, and values made uniform
+// with uni() live in uniform registers: ptxas then feeds tcgen05.mma / tcgen05.commit / cp.async.bulk their
+// uniform-register operands directly instead of wrapping every instruction in an ELECT + R2UR.BROADCAST waterfall
+// loop (which costs ~150 cycles per MMA and made the tensor pipe issue-bound at 13 % busy).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// the same for a lane that runs alone in divergent code (membermask = that lane)
+__device__ __forceinline__ bool elect_lane(uint32_t lane_mask) {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, %1;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred)
+      : "r"(lane_mask));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -146,9 +194,26 @@ struct Params {
   const float *in_scale, *in_shift, *residual;
   float *dst;
   int K, Cin, Cout, KB, in_relu, vec4;
-  int lna, lnw, nrc, nacc, nmma, tmem_cols;  // A ring = 1 << lna stages, W ring = 1 << lnw stages
+  unsigned long long *tl;  // optional timeline buffer (wsis_conv_debug_timeline): [0] = event count, then (time, code)
+  int tl_cap;
+  int dbg;  // WSIS_CONV_DEBUG bits (timing experiments only; results are wrong): 1 no MMA, 2 no build, 4 no gather, 8 no weight copy
+  int lna, lnw, nrc, nrec, nb, nacc, nmma, tmem_cols;
+  int rec_main;  // shared-memory bytes reserved for one entry record (>= the largest meta[t].x of this tile map)  // A ring = 1 << lna stages, W ring = 1 << lnw, nb active builders
   int64_t num_tiles;
 };
+
+// timeline event of CTA 0 (diagnostics only): every role appends to its own 512-entry region (no atomics, stores
+// are fire-and-forget); code = role << 24 | tile iteration << 16 | event << 12 | unit
+__device__ __forceinline__ void tl_event(const Params &p, uint32_t role, uint32_t it, uint32_t ev, uint32_t unit) {
+  if (kDiag && p.tl != nullptr && blockIdx.x == 0 && it < 4) {
+    unsigned long long now;
+    now = (unsigned long long)clock64();  // SM-local cycle counter: all roles of the CTA share it
+    // slot inside the role's region derived from (it, ev, unit): at most 4 tiles x 4 events x 32 units
+    const uint32_t slot = (it * 4 + ev) * 32 + (unit & 31u);
+    p.tl[2 * (role * 512 + slot)] = now;
+    p.tl[2 * (role * 512 + slot) + 1] = (role << 24) | (it << 16) | (ev << 12) | (unit & 0xfffu);
+  }
+}
 
 // relu?(x * sc + sh) -> bf16 hi (part 0) or bf16 mid = bf16(y - hi) (part 1), two values per 32-bit word
 __device__ __forceinline__ uint32_t split2(float a, float b, int part) {
@@ -180,6 +245,19 @@ __device__ __forceinline__ float4 prologue4(float4 x, float4 sc, float4 sh, int 
   return y;
 }
 
+// A tile that reads more distinct rows than a row-cache buffer holds fetches the overflow rows directly: 8 channels
+// [c0, c0 + 8) of unique row `loc` of the tile -> prologue -> 8 bf16 (hi or mid).  Rare; kept out of line.
+__device__ __noinline__ uint4 fetch_direct(const Params &p, int64_t tile, uint32_t loc, int c0, int part,
+                                           const float *s_scale, const float *s_shift) {
+  const int32_t row = __ldg(p.uidx + tile * (int64_t)(kTileM * p.K) + loc);
+  const float4 y0 = prologue4(load_row4(p, row, c0), *reinterpret_cast<const float4 *>(s_scale + c0),
+                              *reinterpret_cast<const float4 *>(s_shift + c0), p.in_relu);
+  const float4 y1 = prologue4(load_row4(p, row, c0 + 4), *reinterpret_cast<const float4 *>(s_scale + c0 + 4),
+                              *reinterpret_cast<const float4 *>(s_shift + c0 + 4), p.in_relu);
+  return make_uint4(split2(y0.x, y0.y, part), split2(y0.z, y0.w, part), split2(y1.x, y1.y, part),
+                    split2(y1.z, y1.w, part));
+}
+
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -203,13 +281,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   constexpr uint32_t row_b = NS * 64;  // one row-cache row: 32 channels of bf16 hi (+ 32 of bf16 mid)
   constexpr uint32_t rc_buf = kRcap * row_b;
   const uint32_t rec_stride = (uint32_t)rec_stride_bytes(p.K);
-  const uint32_t rec_buf = rec_stride + kRcap * 4;  // entry record + the first kRcap unique rows
+  const uint32_t rec_main = (uint32_t)p.rec_main;
+  const uint32_t rec_buf = rec_main + kRcap * 4;  // entry record + the first kRcap unique rows
   const uint32_t hdr_bytes = (uint32_t)rec_hdr_bytes(p.K);
   uint8_t *s_a = sm;                                  // [na][NS][128 x 64 B swizzled]  A operands
   uint8_t *s_w = s_a + (size_t)na * a_stage;          // [nw][NS][Cout x 64 B swizzled] weight blocks (bulk copies)
   uint8_t *s_rc = s_w + (size_t)nw * w_stage;         // [nrc][kRcap][row_b]            converted source rows
-  uint8_t *s_rec = s_rc + (size_t)p.nrc * rc_buf;     // [kNRec][rec_buf]               tile records (bulk copies)
-  float *s_scale = reinterpret_cast<float *>(s_rec + (size_t)kNRec * rec_buf);
+  uint8_t *s_rec = s_rc + (size_t)p.nrc * rc_buf;     // [p.nrec][rec_buf]               tile records (bulk copies)
+  float *s_scale = reinterpret_cast<float *>(s_rec + (size_t)p.nrec * rec_buf);
   float *s_shift = s_scale + KB * kKB;
   uint4 *s_smask = reinterpret_cast<uint4 *>(s_shift + KB * kKB);  // [na] valid-slot mask of the unit in each A stage
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_smask + na);
@@ -223,10 +302,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   auto rce_bar = [&](uint32_t s) { return bar1 + 8u * (p.nrc + s); };
   const uint32_t bar2 = bar1 + 8u * (2 * p.nrc);
   auto recf_bar = [&](uint32_t s) { return bar2 + 8u * s; };
-  auto rece_bar = [&](uint32_t s) { return bar2 + 8u * (kNRec + s); };
-  auto accf_bar = [&](uint32_t s) { return bar2 + 8u * (2 * kNRec + s); };
-  auto acce_bar = [&](uint32_t s) { return bar2 + 8u * (2 * kNRec + 2 + s); };
-  const uint32_t nbars = 2 * na + 2 * nw + 2 * p.nrc + 2 * kNRec + 4;
+  auto rece_bar = [&](uint32_t s) { return bar2 + 8u * (p.nrec + s); };
+  auto accf_bar = [&](uint32_t s) { return bar2 + 8u * (2 * p.nrec + s); };
+  auto acce_bar = [&](uint32_t s) { return bar2 + 8u * (2 * p.nrec + 2 + s); };
+  const uint32_t nbars = 2 * na + 2 * nw + 2 * p.nrc + 2 * p.nrec + 4;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + nbars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -246,11 +325,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     }
     for (int s = 0; s < p.nrc; ++s) {
       mbar_init(rcf_bar(s), kGatherWarps);
-      mbar_init(rce_bar(s), kBuildWarps);
+      mbar_init(rce_bar(s), p.nb);
     }
-    for (int s = 0; s < kNRec; ++s) {
+    for (int s = 0; s < p.nrec; ++s) {
       mbar_init(recf_bar(s), 1);
-      mbar_init(rece_bar(s), kGatherWarps + kBuildWarps);
+      mbar_init(rece_bar(s), kGatherWarps + p.nb);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(accf_bar(s), p.nmma);
@@ -282,15 +361,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
 
   if (warp < kEpiWarps) {
     // ===================== epilogue: TMEM -> registers -> (+residual) -> global, once per tile =====================
+    // Everything that does not depend on the accumulator is in flight before the wait: the tile's destination rows
+    // (fetched one tile ahead) and the residual of the first 16-column chunk; inside the tile the residual of chunk
+    // c + 1 is fetched while chunk c is read out of TMEM.
     uint32_t as = 0, aph = 0;
+    int32_t rid = __ldg(p.order + (int64_t)blockIdx.x * kTileM + warp * 32 + lane);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int32_t rid = __ldg(p.order + tile * kTileM + warp * 32 + lane);
-      mbar_wait(accf_bar(as), aph);
-      tc_fence_after();
       const int64_t row = rid;
       const bool live = rid >= 0;
+      const int64_t nxt = tile + gridDim.x;
+      if (nxt < p.num_tiles) rid = __ldg(p.order + nxt * kTileM + warp * 32 + lane);
+      const bool has_res = live && p.residual != nullptr;
+      const float4 *rs = reinterpret_cast<const float4 *>(p.residual + (has_res ? row * p.Cout : 0));
+      float4 r4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r4[q] = has_res ? __ldg(rs + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(accf_bar(as), aph);
+      tc_fence_after();
+      if (tid == 0) tl_event(p, 0, (uint32_t)((tile - blockIdx.x) / gridDim.x), 0, 0);
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * (uint32_t)(p.nacc * p.Cout);
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+      for (int c0 = 0; c0 < p.Cout && !WSIS_DBG(32); c0 += 16) {
+        float4 rn[4];
+        const bool more = c0 + 16 < p.Cout;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          rn[q] = (has_res && more) ? __ldg(rs + (c0 + 16) / 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         float v[16];
         tmem_ld16(taddr + c0, v);
         tmem_zero16(taddr + c0);  // hand the accumulator back cleared
@@ -303,24 +398,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         }
         if (live) {
           float4 *o = reinterpret_cast<float4 *>(p.dst + row * p.Cout + c0);
-          if (p.residual) {
-            const float4 *rs = reinterpret_cast<const float4 *>(p.residual + row * p.Cout + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 r4 = __ldg(rs + q);
-              v[4 * q] += r4.x;
-              v[4 * q + 1] += r4.y;
-              v[4 * q + 2] += r4.z;
-              v[4 * q + 3] += r4.w;
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; ++q)
+            o[q] = make_float4(v[4 * q] + r4[q].x, v[4 * q + 1] + r4[q].y, v[4 * q + 2] + r4[q].z,
+                               v[4 * q + 3] + r4[q].w);
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r4[q] = rn[q];
       }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(acce_bar(as));
+      if (tid == 0) tl_event(p, 0, (uint32_t)((tile - blockIdx.x) / gridDim.x), 1, 0);
       if (++as == 2) {
         as = 0;
         aph ^= 1;
@@ -337,29 +426,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     const int rsub = gt >> 3, chunk = gt & 7;
     uint32_t it = 0, q = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t rb = it % kNRec;
-      mbar_wait(recf_bar(rb), (it / kNRec) & 1);
+      const uint32_t rb = it % p.nrec;
+      mbar_wait(recf_bar(rb), (it / p.nrec) & 1);
+      if (gt == 0) tl_event(p, 1, it, 0, 0);
       const uint8_t *rec = s_rec + (size_t)rb * rec_buf;
-      const int nU = reinterpret_cast<const uint16_t *>(rec + 16 * p.K)[p.K + 1];
-      const int ng = min(nU, kRcap);
-      const int32_t *s_uidx = reinterpret_cast<const int32_t *>(rec + rec_stride);
+      // distinct rows of the tile (the overflow beyond a row-cache buffer is fetched directly by the builders)
+      const int ng = min((int)reinterpret_cast<const uint16_t *>(rec + 16 * p.K)[p.K + 1], kRcap);
+      const int32_t *uidx = reinterpret_cast<const int32_t *>(rec + rec_main);
       for (int kb = 0; kb < KB; ++kb, ++q) {
         const uint32_t slot = q % p.nrc;
-        mbar_wait(rce_bar(slot), ((q / p.nrc) & 1) ^ 1);
-        uint8_t *rcb = s_rc + (size_t)slot * rc_buf;
         const int c0 = kb * kKB + chunk * 4;
         const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c0);
         const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c0);
-        for (int u0 = 0; u0 < ng; u0 += 128) {
-          float4 v[8];
+        uint8_t *rcb = s_rc + (size_t)slot * rc_buf;
+        bool waited = false;
+        constexpr int kSweep = kGatherWarps * 4;  // rows per load instruction of the gather warps
+        constexpr int kInFlight = 8;              // 16-byte loads in flight per gather lane
+        for (int u0 = 0; u0 < ng; u0 += kInFlight * kSweep) {
+          int32_t idx[kInFlight];
+          float4 v[kInFlight];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int u = u0 + i * 16 + rsub;
-            if (u < ng) v[i] = load_row4(p, s_uidx[u], c0);
+          for (int i = 0; i < kInFlight; ++i) {
+            const int u = u0 + i * kSweep + rsub;
+            if (u < ng) idx[i] = uidx[u];
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int u = u0 + i * 16 + rsub;
+          for (int i = 0; i < kInFlight; ++i) {
+            const int u = u0 + i * kSweep + rsub;
+            if (u < ng && !WSIS_DBG(4)) v[i] = load_row4(p, idx[i], c0);
+          }
+          if (gt == 0) tl_event(p, 1, it, 1, (uint32_t)kb);
+          if (!waited) {  // the loads are in flight while the buffer drains
+            mbar_wait(rce_bar(slot), ((q / p.nrc) & 1) ^ 1);
+            waited = true;
+          }
+          if (gt == 0) tl_event(p, 1, it, 2, (uint32_t)kb);
+#pragma unroll
+          for (int i = 0; i < kInFlight; ++i) {
+            const int u = u0 + i * kSweep + rsub;
             if (u < ng) {
               const float4 y = prologue4(v[i], sc, sh, p.in_relu);
               if (NS == 2) {
@@ -378,8 +482,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
             }
           }
         }
+        if (!waited) mbar_wait(rce_bar(slot), ((q / p.nrc) & 1) ^ 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(rcf_bar(slot));
+        if (gt == 0) tl_event(p, 1, it, 3, (uint32_t)kb);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(rece_bar(rb));  // this warp no longer reads s_rec[rb]
@@ -387,17 +493,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   } else if (warp < kMmaWarp0) {
     // ===================== builders: one WARP per pipeline unit, shared memory -> shared memory =====================
     // Unit = (32-channel block kb, active kernel offset k) of a tile; the CTA's j-th unit lives in A stage j % na and
-    // is assembled by builder warp j % kBuildWarps: the entries of offset k copy their converted row from the row
-    // cache into the 64B-swizzled K-major block the UMMA descriptor expects, at the row of their tile slot.
+    // is assembled by builder warp j % nb: the entries of offset k copy their converted row from the row cache into
+    // the 64B-swizzled K-major block the UMMA descriptor expects, at the row of their tile slot.
+    // nb <= na (and both even when two issuers split the units): a builder moves from unit j to j + nb, and a parity
+    // wait on a stage's empty barrier is only unambiguous while that is at most one ring generation ahead of the
+    // (per-issuer in-order) commits.
     const int b = warp - (kEpiWarps + kGatherWarps);
+    const uint32_t nb = (uint32_t)p.nb;
     constexpr int LPE = 4 * NS;    // lanes per entry (16 bytes each: 4 hi chunks [+ 4 mid chunks])
     constexpr int EPI = 32 / LPE;  // entries per warp instruction
     const int e_in = lane / LPE, l = lane % LPE, part = l >> 2, c16 = l & 3;
     const uint32_t s_a32 = smem_u32(s_a), s_rc32 = smem_u32(s_rc);
     uint32_t it = 0, q = 0, j0 = 0;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t rb = it % kNRec;
-      mbar_wait(recf_bar(rb), (it / kNRec) & 1);
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles && (uint32_t)b < nb; tile += gridDim.x, ++it) {
+      const uint32_t rb = it % p.nrec;
+      mbar_wait(recf_bar(rb), (it / p.nrec) & 1);
       const uint8_t *rec = s_rec + (size_t)rb * rec_buf;
       const uint16_t *start = reinterpret_cast<const uint16_t *>(rec + 16 * p.K);
       const int P = start[p.K];
@@ -413,47 +523,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         mbar_wait(rcf_bar(slot), (q / p.nrc) & 1);
         const uint32_t rcb = s_rc32 + slot * rc_buf;
         const uint32_t jb = j0 + (uint32_t)kb * nact;
-        for (uint32_t ak = ((uint32_t)b + kBuildWarps - jb % kBuildWarps) % kBuildWarps; ak < nact; ak += kBuildWarps) {
+        uint32_t ak = ((uint32_t)b + nb - jb % nb) % nb;
+        uint32_t mm = mask;  // lowest set bit of mm = the ak-th active offset
+        for (uint32_t i = 0; i < ak; ++i) mm &= mm - 1;
+        for (; ak < nact; ak += nb) {
           const uint32_t j = jb + ak;
           const uint32_t stage = j & (na - 1), phase = (j >> p.lna) & 1;
-          const int k = __fns(mask, 0, ak + 1);  // ak-th active offset
+          const int k = __ffs(mm) - 1;
+          for (uint32_t i = 0; i < nb; ++i) mm &= mm - 1;
           const int s0 = start[k], n = start[k + 1] - s0;
-          mbar_wait(aempty_bar(stage), phase ^ 1);
-          if (lane == 0) s_smask[stage] = *reinterpret_cast<const uint4 *>(rec + 16 * k);
-          const uint32_t abase = s_a32 + stage * a_stage + (uint32_t)part * kABlockBytes;
-          for (int e0 = 0; e0 < n; e0 += 4 * EPI) {
-            uint4 v[4];
-            uint32_t off[4];
+          // Before the stage is free: fetch this lane's share of the unit (entry -> row-cache row -> registers), so
+          // that the stage's critical path (commit -> builder -> issuer) is only store + fence + arrive.
+          constexpr int PF = 4;
+          uint4 v[PF];
+          uint32_t off[PF];
+          const uint32_t xl = (uint32_t)l;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int e = e0 + i * EPI + e_in;
-              if (e < n) {
-                const uint32_t loc = eloc[s0 + e];
-                off[i] = sw64(eslot[s0 + e], c16);
-                if (loc < kRcap) {
-                  v[i] = lds128(rcb + loc * row_b + ((NS == 2 ? ((uint32_t)l ^ ((loc & 1u) << 2)) : (uint32_t)l) << 4));
-                } else {
-                  // the tile reads more distinct rows than a row-cache buffer holds: fetch this one directly
-                  const int32_t row = __ldg(p.uidx + tile * (int64_t)(kTileM * p.K) + loc);
-                  const int c0 = kb * kKB + c16 * 8;
-                  const float4 y0 = prologue4(load_row4(p, row, c0), *reinterpret_cast<const float4 *>(s_scale + c0),
-                                              *reinterpret_cast<const float4 *>(s_shift + c0), p.in_relu);
-                  const float4 y1 = prologue4(load_row4(p, row, c0 + 4), *reinterpret_cast<const float4 *>(s_scale + c0 + 4),
-                                              *reinterpret_cast<const float4 *>(s_shift + c0 + 4), p.in_relu);
-                  v[i] = make_uint4(split2(y0.x, y0.y, part), split2(y0.z, y0.w, part), split2(y1.x, y1.y, part),
-                                    split2(y1.z, y1.w, part));
-                }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int e = e0 + i * EPI + e_in;
-              if (e < n) sts128(abase + off[i], v[i]);
+          for (int i = 0; i < PF; ++i) {
+            const int e = i * EPI + e_in;
+            if (e < n && !WSIS_DBG(2)) {
+              const uint32_t loc = eloc[s0 + e];
+              off[i] = sw64(eslot[s0 + e], c16);
+              if (loc < kRcap)
+                v[i] = lds128(rcb + loc * row_b + ((NS == 2 ? (xl ^ ((loc & 1u) << 2)) : xl) << 4));
+              else
+                v[i] = fetch_direct(p, tile, loc, kb * kKB + c16 * 8, part, s_scale, s_shift);
             }
           }
-          fence_proxy_async();
+          if (lane == 0) tl_event(p, 2 + b, it, 0, j - j0);
+          mbar_wait(aempty_bar(stage), phase ^ 1);
+          if (lane == 0) tl_event(p, 2 + b, it, 1, j - j0);
+          if (lane == 0) s_smask[stage] = *reinterpret_cast<const uint4 *>(rec + 16 * k);
+          const uint32_t abase = s_a32 + stage * a_stage + (uint32_t)part * kABlockBytes;
+#pragma unroll
+          for (int i = 0; i < PF; ++i)
+            if (i * EPI + e_in < n && !WSIS_DBG(2)) sts128(abase + off[i], v[i]);
+          for (int e = PF * EPI + e_in; e < n; e += EPI) {  // long units (dense neighbourhoods)
+            const uint32_t loc = eloc[s0 + e];
+            const uint32_t o = sw64(eslot[s0 + e], c16);
+            uint4 w;
+            if (loc < kRcap)
+              w = lds128(rcb + loc * row_b + ((NS == 2 ? (xl ^ ((loc & 1u) << 2)) : xl) << 4));
+            else
+              w = fetch_direct(p, tile, loc, kb * kKB + c16 * 8, part, s_scale, s_shift);
+            sts128(abase + o, w);
+          }
+          if (!WSIS_DBG(128)) fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(afull_bar(stage));
+          if (lane == 0) tl_event(p, 2 + b, it, 2, j - j0);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(rce_bar(slot));  // this warp no longer reads row-cache buffer `slot`
@@ -468,93 +586,106 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     // own TMEM accumulators: M=128 x N=Cout x K=16 MMAs are short (N/2 cycles), so a single dependent accumulate
     // chain issued by a single thread is bound by the MMA pipeline latency and the per-unit barrier handling, not by
     // the tensor pipe.  Independent chains (nacc accumulators, summed by the epilogue) and two issuers hide both.
-    const int mi = warp - kMmaWarp0;
-    if (lane == 0 && mi < p.nmma) {
+    // The whole warp runs the (warp-uniform) loop; one elected lane issues.
+    const uint32_t mi = uni((uint32_t)(warp - kMmaWarp0));
+    if (mi < (uint32_t)p.nmma) {
+      const uint32_t nmma = (uint32_t)p.nmma;
+      const uint32_t tbase = uni(tmem_base);
       const uint32_t idesc = make_idesc(p.Cout);
-      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w), m_base = smem_u32(s_smask);
       const uint64_t desc0 = make_desc(0);
       uint32_t j0 = 0;
       uint32_t as = 0, aph = 0;
-      const uint32_t per = (uint32_t)(p.nacc / p.nmma);  // accumulators of this issuer: mi, mi + nmma, ...
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const uint32_t n = (uint32_t)__popc((uint32_t)__ldg(p.meta + tile).z) * (uint32_t)KB;
+      const uint32_t per = (uint32_t)p.nacc / nmma;  // accumulators of this issuer: mi, mi + nmma, ...
+      uint32_t itx = 0;
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++itx) {
+        const uint32_t n = uni((uint32_t)__popc((uint32_t)__ldg(&p.meta[tile].z))) * (uint32_t)KB;
         mbar_wait(acce_bar(as), aph ^ 1);
         tc_fence_after();
-        const uint32_t d_base = tmem_base + as * (uint32_t)(p.nacc * p.Cout);
-        const uint32_t d0 = d_base + mi * p.Cout, d1 = per > 1 ? d0 + p.nmma * p.Cout : d0;
-        for (uint32_t u = ((uint32_t)mi - j0) & (uint32_t)(p.nmma - 1); u < n; u += p.nmma) {
+        const uint32_t d_base = tbase + as * (uint32_t)(p.nacc * p.Cout);
+        const uint32_t d0 = d_base + mi * p.Cout, d1 = per > 1 ? d0 + nmma * p.Cout : d0;
+        for (uint32_t u = (mi - j0) & (nmma - 1); u < n; u += nmma) {
           const uint32_t j = j0 + u;
           const uint32_t sa = j & (na - 1), sw = j & (nw - 1);
           mbar_wait(afull_bar(sa), (j >> p.lna) & 1);
-          mbar_wait(wfull_bar(sw), (j >> p.lnw) & 1);
+          if (lane == 0) tl_event(p, 16 + mi, itx, 0, u);
+          if (!WSIS_DBG(16)) mbar_wait(wfull_bar(sw), (j >> p.lnw) & 1);
           tc_fence_after();
-          uint4 vm;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(vm.x), "=r"(vm.y), "=r"(vm.z), "=r"(vm.w)
-                       : "r"(smem_u32(s_smask + sa))
-                       : "memory");
-          const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
+          if (lane == 0) tl_event(p, 16 + mi, itx, 1, u);
           const uint64_t ad = desc0 + ((a_base + sa * a_stage) >> 4), bd = desc0 + ((w_base + sw * w_stage) >> 4);
-          if ((vm.x | vm.y | vm.z | vm.w) != 0) {
-            // accumulators of this issuer alternate between consecutive MMAs (independent chains)
-            mma_bf16(d0, ad, bd, idesc, off);
-            if (NS == 2) {
-              mma_bf16(d1, ad, bd + (b_block >> 4), idesc, off);
-              mma_bf16(d0, ad + (kABlockBytes >> 4), bd, idesc, off);
+          if (elect_one()) {
+            const uint4 vm = lds128(m_base + sa * 16);  // valid-slot mask of the unit; the MMA takes its complement
+            const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
+            if ((vm.x | vm.y | vm.z | vm.w) != 0 && !WSIS_DBG(1)) {
+              // accumulators of this issuer alternate between consecutive MMAs (independent chains)
+              mma_bf16(d0, ad, bd, idesc, off);
+              if (NS == 2) {
+                mma_bf16(d1, ad, bd + (b_block >> 4), idesc, off);
+                mma_bf16(d0, ad + (kABlockBytes >> 4), bd, idesc, off);
+              }
+              mma_bf16(d1, ad + 2, bd + 2, idesc, off);
+              if (NS == 2) {
+                mma_bf16(d0, ad + 2, bd + (b_block >> 4) + 2, idesc, off);
+                mma_bf16(d1, ad + (kABlockBytes >> 4) + 2, bd + 2, idesc, off);
+              }
             }
-            mma_bf16(d1, ad + 2, bd + 2, idesc, off);
-            if (NS == 2) {
-              mma_bf16(d0, ad + 2, bd + (b_block >> 4) + 2, idesc, off);
-              mma_bf16(d1, ad + (kABlockBytes >> 4) + 2, bd + 2, idesc, off);
-            }
+            if WSIS_DBG(64) mbar_arrive(aempty_bar(sa)); else mma_commit(aempty_bar(sa));
+            if (!WSIS_DBG(16)) mma_commit(wempty_bar(sw));
           }
-          mma_commit(aempty_bar(sa));
-          mma_commit(wempty_bar(sw));
+          __syncwarp();
+          if (lane == 0) tl_event(p, 16 + mi, itx, 2, u);
         }
         j0 += n;
-        mma_commit(accf_bar(as));
+        if (elect_one()) mma_commit(accf_bar(as));
+        __syncwarp();
         if (++as == 2) {
           as = 0;
           aph ^= 1;
         }
       }
     }
-    __syncwarp();
   } else if (warp == kMmaWarp0 + kMmaWarps) {
-    // ===================== record producer: bulk copies of each tile's record, kNRec - 1 tiles ahead ===============
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t rb = it % kNRec;
-        const int4 m = __ldg(p.meta + tile);
-        const uint32_t ub = ((uint32_t)min(m.y, kRcap) * 4u + 15u) & ~15u;
-        mbar_wait(rece_bar(rb), ((it / kNRec) & 1) ^ 1);
-        mbar_expect_tx(recf_bar(rb), (uint32_t)m.x + ub);
-        const uint32_t dst = smem_u32(s_rec + (size_t)rb * rec_buf);
-        bulk_g2s(dst, p.recs + tile * (int64_t)rec_stride, (uint32_t)m.x, recf_bar(rb));
-        if (ub) bulk_g2s(dst + rec_stride, p.uidx + tile * (int64_t)(kTileM * p.K), ub, recf_bar(rb));
+    // ===================== record producer: bulk copies of each tile's record, p.nrec - 1 tiles ahead ===============
+    uint32_t it = 0;
+    const uint32_t rec0 = smem_u32(s_rec);
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t rb = it % p.nrec;
+      const int4 m = __ldg(p.meta + tile);
+      const uint32_t nbytes = uni((uint32_t)m.x);
+      const uint32_t ub = (min(uni((uint32_t)m.y), (uint32_t)kRcap) * 4u + 15u) & ~15u;
+      mbar_wait(rece_bar(rb), ((it / p.nrec) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(recf_bar(rb), nbytes + ub);
+        const uint32_t dst = rec0 + rb * rec_buf;
+        bulk_g2s(dst, p.recs + tile * (int64_t)rec_stride, nbytes, recf_bar(rb));
+        if (ub) bulk_g2s(dst + rec_main, p.uidx + tile * (int64_t)(kTileM * p.K), ub, recf_bar(rb));
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== weight producer: bulk copy of each unit's pre-swizzled weight block, nw units ahead =====
-    if (lane == 0) {
-      uint32_t j = 0;
-      const uint32_t w_base = smem_u32(s_w);
-      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const uint32_t mask = (uint32_t)__ldg(p.meta + tile).z;
-        for (int kb = 0; kb < KB; ++kb) {
-          for (uint32_t mm = mask; mm; mm &= mm - 1, ++j) {
-            const int k = __ffs(mm) - 1;
-            const uint32_t sw = j & (nw - 1);
-            mbar_wait(wempty_bar(sw), ((j >> p.lnw) & 1) ^ 1);
-            mbar_expect_tx(wfull_bar(sw), w_stage);
-            bulk_g2s(w_base + sw * w_stage, p.packed + (size_t)(k * KB + kb) * w_stage, w_stage, wfull_bar(sw));
+    uint32_t j = 0;
+    const uint32_t w_base = smem_u32(s_w);
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles && !WSIS_DBG(16); tile += gridDim.x) {
+      const uint32_t mask = uni((uint32_t)__ldg(&p.meta[tile].z));
+      for (int kb = 0; kb < KB; ++kb) {
+        for (uint32_t mm = mask; mm; mm &= mm - 1, ++j) {
+          const int k = __ffs(mm) - 1;
+          const uint32_t sw = j & (nw - 1);
+          mbar_wait(wempty_bar(sw), ((j >> p.lnw) & 1) ^ 1);
+          if (lane == 0) tl_event(p, 24, 0, 0, j);
+          if (elect_one()) {
+            if WSIS_DBG(8) {
+              mbar_arrive(wfull_bar(sw));
+            } else {
+              mbar_expect_tx(wfull_bar(sw), w_stage);
+              bulk_g2s(w_base + sw * w_stage, p.packed + (size_t)(k * KB + kb) * w_stage, w_stage, wfull_bar(sw));
+            }
           }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -595,7 +726,16 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int K, int Cin,
 using namespace wsis;
 using namespace wsis::umma;
 
+static unsigned long long *g_tl = nullptr;
+static int g_tl_cap = 0;
+
 extern "C" {
+
+int wsis_conv_debug_timeline(void *buf, int capacity) {
+  g_tl = reinterpret_cast<unsigned long long *>(buf);
+  g_tl_cap = capacity;
+  return 0;
+}
 
 int wsis_conv_umma_supported(int Cin, int Cout) {
   return Cin >= 1 && Cin <= 1024 && Cout >= 16 && Cout % 16 == 0 && Cout <= 256;
@@ -620,7 +760,8 @@ int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpo
 }
 
 int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, const int32_t *meta,
-                   const int32_t *order, int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
+                   const int32_t *order, int64_t num_tiles, int K, int max_record_bytes, const void *packed, int Cin,
+                   int Cout, int precision,
                    const float *in_scale, const float *in_shift, int in_relu, const float *residual, float *dst,
                    wsis_stream_t stream) {
   WSIS_CHECK(wsis_conv_umma_supported(Cin, Cout), "conv_umma: unsupported Cin=%d Cout=%d", Cin, Cout);
@@ -651,30 +792,46 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, c
   p.in_relu = in_relu;
   p.vec4 = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   p.num_tiles = num_tiles;
-  // independent accumulate chains per accumulator buffer: as many as the 512 TMEM columns allow, up to 4
-  int nacc = 4;
+  p.tl = g_tl;
+  p.tl_cap = g_tl_cap;
+  {
+    const char *d = getenv("WSIS_CONV_DEBUG");
+    p.dbg = d ? atoi(d) : 0;
+  }
+  // one accumulate chain (TMEM accumulator) per issuer, as far as the 512 TMEM columns allow
+  int nacc = kMmaWarps;
   while (nacc > 1 && 2 * nacc * Cout > 512) nacc >>= 1;
   p.nacc = nacc;
-  p.nmma = nacc >= 2 ? kMmaWarps : 1;
+  p.nmma = std::min(nacc, kMmaWarps);  // one accumulate chain per issuer (two when nacc > nmma)
   int cols = 32;
   while (cols < 2 * nacc * Cout) cols <<= 1;
   p.tmem_cols = cols;
   // shared memory: A ring (2^lna stages), weight ring (2^lnw), row cache (nrc buffers), records; shrink the rings
   // in this order of preference until the layer fits
   const int64_t a_stage = (int64_t)NS * kABlockBytes, w_stage = (int64_t)NS * Cout * 64;
-  const int64_t rc_buf = (int64_t)kRcap * NS * 64, rec_buf = rec_stride_bytes(K) + kRcap * 4;
-  static const int pref[][3] = {{2, 3, 3}, {2, 2, 3}, {2, 3, 2}, {2, 2, 2}, {1, 2, 2}, {1, 1, 2}, {1, 1, 1}};
-  const int64_t budget = 226 * 1024;
+  // the record buffers are sized for the largest record of THIS tile map when the caller knows it (0 = worst case)
+  WSIS_CHECK(max_record_bytes >= 0 && max_record_bytes % 16 == 0 && max_record_bytes <= rec_stride_bytes(K),
+             "conv_umma: max_record_bytes %d must be a multiple of 16 in [0, %d]", max_record_bytes, rec_stride_bytes(K));
+  p.rec_main = max_record_bytes ? max_record_bytes : rec_stride_bytes(K);
+  const int64_t rc_buf = (int64_t)kRcap * NS * 64, rec_buf = p.rec_main + kRcap * 4;
+  static const int pref[][3] = {{3, 3, 3}, {3, 3, 2}, {3, 2, 2}, {2, 3, 3}, {2, 3, 2}, {2, 2, 2}, {1, 2, 2}, {1, 1, 2}, {1, 1, 1}};
+  const int64_t budget = 227 * 1024;
+  {
+    const char *d = getenv("WSIS_CONV_NREC");
+    p.nrec = d ? std::max(2, std::min(kMaxRec, atoi(d))) : 2;
+  }
   int64_t smem = 0;
   bool fit = false;
   for (auto &c : pref) {
     const int na = 1 << c[0], nw = 1 << c[1], nrc = c[2];
-    const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nw + 2 * nrc + 2 * kNRec + 4) * 8 + 64;
-    smem = misc + na * a_stage + nw * w_stage + nrc * rc_buf + kNRec * rec_buf;
+    const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nw + 2 * nrc + 2 * p.nrec + 4) * 8 + 64;
+    smem = misc + na * a_stage + nw * w_stage + nrc * rc_buf + p.nrec * rec_buf;
     if (smem <= budget) {
       p.lna = c[0];
       p.lnw = c[1];
       p.nrc = nrc;
+      p.nb = std::min(kBuildWarps, na);
+      p.nmma = std::min(p.nmma, na);  // every A/W stage belongs to exactly one issuer
       fit = true;
       break;
     }

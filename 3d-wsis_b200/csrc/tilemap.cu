@@ -60,7 +60,8 @@ __device__ __forceinline__ uint32_t tile_hash(int32_t v, uint32_t mask) {
 
 __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__restrict__ map, int K, int flip, int HT,
                                                             const int32_t *__restrict__ order, uint8_t *__restrict__ recs,
-                                                            int32_t *__restrict__ uidx, int4 *__restrict__ meta) {
+                                                            int32_t *__restrict__ uidx, int4 *__restrict__ meta,
+                                                            int32_t *__restrict__ stats) {
   extern __shared__ int32_t s_map[];  // [K][128] transposed slice
   int32_t *s_cnt = s_map + K * kTile;                                   // [4K + 1] entry prefix, [4] table prefix
   int32_t *s_tab = s_cnt + 4 * K + 8;                                   // [HT] open-addressing set of source rows
@@ -144,6 +145,8 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
     for (int k = 0; k < K; ++k)
       if (s_cnt[(k + 1) * 4] > s_cnt[k * 4]) am |= 1u << k;
     meta[t] = make_int4((rec_hdr_bytes(K) + 3 * P + 15) & ~15, nU, (int)(am ? am : 1u), P);
+    atomicMax(stats, (rec_hdr_bytes(K) + 3 * P + 15) & ~15);  // largest record / most distinct rows of the map
+    atomicMax(stats + 1, nU);
   }
 }
 
@@ -216,8 +219,9 @@ static int tile_table_slots(int K) {
 }
 
 int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const int32_t *order, void *records,
-                      int32_t *uidx, int32_t *meta, wsis_stream_t stream) {
+                      int32_t *uidx, int32_t *meta, int32_t *stats, wsis_stream_t stream) {
   const int64_t n_tiles = wsis_tile_pad(n_rows) / kTile;
+  WSIS_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(int32_t), as_stream(stream)));
   if (n_tiles == 0) return 0;
   WSIS_CHECK(K >= 1 && K <= 32, "tile_records: kernel volume %d not in [1,32]", K);
   WSIS_CHECK(((reinterpret_cast<uintptr_t>(records) | reinterpret_cast<uintptr_t>(uidx) |
@@ -231,7 +235,7 @@ int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const
     smem_set = smem;
   }
   tile_record_kernel<<<(unsigned)n_tiles, kTile, smem, as_stream(stream)>>>(
-      map, K, flip, HT, order, (uint8_t *)records, uidx, reinterpret_cast<int4 *>(meta));
+      map, K, flip, HT, order, (uint8_t *)records, uidx, reinterpret_cast<int4 *>(meta), stats);
   WSIS_LAUNCH_OK();
   return 0;
 }

@@ -127,6 +127,8 @@ int wsis_conv_simt(const float *src, const int32_t *map, int64_t n_dst, int K, i
  *     DISTINCT source rows, eslot = tile slot (ascending inside an offset); valid[k] = slots that have an entry
  *   uidx + t * wsis_tile_unique_stride(K): int32[nU] the distinct source rows of the tile (any order)
  *   meta[t] = int32[4] {meaningful record bytes, nU, mask of offsets with an entry (1 if none at all), P}
+ *   stats = int32[2] {largest meaningful record bytes, largest nU} over the tiles (lets the conv kernel size its
+ *   shared-memory record buffers for this map instead of the worst case)
  * records: uint8[num_tiles * stride], uidx: int32[num_tiles * unique_stride], meta: int32[num_tiles * 4], all 16-byte
  * aligned.  K <= 32. */
 int64_t wsis_tile_pad(int64_t n);
@@ -137,20 +139,28 @@ int wsis_identity_order(int64_t N, int32_t *order, wsis_stream_t stream);
 int64_t wsis_tile_record_stride(int K);
 int64_t wsis_tile_unique_stride(int K);
 int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const int32_t *order, void *records,
-                      int32_t *uidx, int32_t *meta, wsis_stream_t stream);
+                      int32_t *uidx, int32_t *meta, int32_t *stats, wsis_stream_t stream);
 
 /* tcgen05 tensor-core path over tile records (num_tiles = wsis_tile_pad(n_dst)/128).  precision: 1 = bf16 operands
  * (1e-2 contract), 3 = bf16x3 split operands with fp32 accumulation in TMEM (1e-4 contract).
  * Requires Cout % 16 == 0, 16 <= Cout <= 256, K <= 32; any Cin (channels are zero-padded to a multiple of 32 inside
- * the kernel and in the packed weights; rows are read with 16-byte loads when Cin % 4 == 0 and src is aligned). */
+ * the kernel and in the packed weights; rows are read with 16-byte loads when Cin % 4 == 0 and src is aligned).
+ * max_record_bytes = stats[0] of wsis_tile_records when the caller has read it back, else 0 (worst case: fewer
+ * pipeline stages fit in shared memory). */
 int wsis_conv_umma_supported(int Cin, int Cout);
 int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision);
 int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
                            wsis_stream_t stream);
 int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, const int32_t *meta,
-                   const int32_t *order, int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
+                   const int32_t *order, int64_t num_tiles, int K, int max_record_bytes, const void *packed, int Cin,
+                   int Cout, int precision,
                    const float *in_scale, const float *in_shift, int in_relu, const float *residual, float *dst,
                    wsis_stream_t stream);
+
+/* Diagnostics: when buf != NULL, CTA 0 of every following wsis_conv_umma launch appends (globaltimer ns, event code)
+ * pairs of its first tiles to buf = uint64[2 * capacity], capacity >= 32 * 512 (one 512-entry region per role; zero it
+ * first, entries with time 0 are unused).  NULL disables. */
+int wsis_conv_debug_timeline(void *buf, int capacity);
 
 /* dW[k] = sum_r prologue(src[map[r,k']])^T . g[r]   (fp32, dW is zeroed by the call). */
 int wsis_conv_wgrad(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const float *g, int Cin,
