@@ -40,8 +40,8 @@ namespace umma {
 constexpr int kTileM = 128;
 constexpr int kKB = 32;                    // channels per pipeline unit (64 bytes of bf16 = one swizzle-64 row)
 constexpr int kABlockBytes = kTileM * 64;  // 8 KB
-constexpr int kEpiWarps = 4, kGatherWarps = 4, kBuildWarps = 4, kMmaWarps = 2, kProdWarps = 2;
-constexpr int kThreads = (kEpiWarps + kGatherWarps + kBuildWarps + kMmaWarps + kProdWarps) * 32;  // 512
+constexpr int kEpiWarps = 4, kGatherWarps = 4, kBuildWarps = 8, kMmaWarps = 2, kProdWarps = 2;
+constexpr int kThreads = (kEpiWarps + kGatherWarps + kBuildWarps + kMmaWarps + kProdWarps) * 32;  // 640
 constexpr int kMaxRec = 4;  // tile records in flight (p.nrec <= kMaxRec)
 constexpr int kRcap = 256;  // rows of one row-cache buffer (a surface tile reads ~160-230 distinct rows)
 
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   }
   if (tid == 0) {
     for (uint32_t s = 0; s < na; ++s) {
-      mbar_init(afull_bar(s), 1);   // the builder warp of the unit
+      mbar_init(afull_bar(s), 2);   // the two builder warps of the unit (each assembles half of its entries)
       mbar_init(aempty_bar(s), 1);  // tcgen05.commit
     }
     for (uint32_t s = 0; s < nw; ++s) {
@@ -325,11 +325,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     }
     for (int s = 0; s < p.nrc; ++s) {
       mbar_init(rcf_bar(s), kGatherWarps);
-      mbar_init(rce_bar(s), p.nb);
+      mbar_init(rce_bar(s), 2 * p.nb);
     }
     for (int s = 0; s < p.nrec; ++s) {
       mbar_init(recf_bar(s), 1);
-      mbar_init(rece_bar(s), kGatherWarps + p.nb);
+      mbar_init(rece_bar(s), kGatherWarps + 2 * p.nb);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(accf_bar(s), p.nmma);
@@ -498,14 +498,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     // nb <= na (and both even when two issuers split the units): a builder moves from unit j to j + nb, and a parity
     // wait on a stage's empty barrier is only unambiguous while that is at most one ring generation ahead of the
     // (per-issuer in-order) commits.
-    const int b = warp - (kEpiWarps + kGatherWarps);
+    // Two warps share a unit (even / odd groups of its entries): dense neighbourhoods have 50-128 entries per unit and
+    // one warp per unit made the builders, not the issuers, the slowest stage on the coarser U-Net levels.
     const uint32_t nb = (uint32_t)p.nb;
+    const int bw = warp - (kEpiWarps + kGatherWarps);
+    const int b = bw % (int)nb, half = bw / (int)nb;
     constexpr int LPE = 4 * NS;    // lanes per entry (16 bytes each: 4 hi chunks [+ 4 mid chunks])
     constexpr int EPI = 32 / LPE;  // entries per warp instruction
     const int e_in = lane / LPE, l = lane % LPE, part = l >> 2, c16 = l & 3;
     const uint32_t s_a32 = smem_u32(s_a), s_rc32 = smem_u32(s_rc);
     uint32_t it = 0, q = 0, j0 = 0;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles && (uint32_t)b < nb; tile += gridDim.x, ++it) {
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles && half < 2; tile += gridDim.x, ++it) {
       const uint32_t rb = it % p.nrec;
       mbar_wait(recf_bar(rb), (it / p.nrec) & 1);
       const uint8_t *rec = s_rec + (size_t)rb * rec_buf;
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
           const uint32_t xl = (uint32_t)l;
 #pragma unroll
           for (int i = 0; i < PF; ++i) {
-            const int e = i * EPI + e_in;
+            const int e = (2 * i + half) * EPI + e_in;
             if (e < n && !WSIS_DBG(2)) {
               const uint32_t loc = eloc[s0 + e];
               off[i] = sw64(eslot[s0 + e], c16);
@@ -553,12 +556,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
           if (lane == 0) tl_event(p, 2 + b, it, 0, j - j0);
           mbar_wait(aempty_bar(stage), phase ^ 1);
           if (lane == 0) tl_event(p, 2 + b, it, 1, j - j0);
-          if (lane == 0) s_smask[stage] = *reinterpret_cast<const uint4 *>(rec + 16 * k);
+          if (lane == 0 && half == 0) s_smask[stage] = *reinterpret_cast<const uint4 *>(rec + 16 * k);
           const uint32_t abase = s_a32 + stage * a_stage + (uint32_t)part * kABlockBytes;
 #pragma unroll
           for (int i = 0; i < PF; ++i)
-            if (i * EPI + e_in < n && !WSIS_DBG(2)) sts128(abase + off[i], v[i]);
-          for (int e = PF * EPI + e_in; e < n; e += EPI) {  // long units (dense neighbourhoods)
+            if ((2 * i + half) * EPI + e_in < n && !WSIS_DBG(2)) sts128(abase + off[i], v[i]);
+          for (int e = (2 * PF + half) * EPI + e_in; e < n; e += 2 * EPI) {  // long units (dense neighbourhoods)
             const uint32_t loc = eloc[s0 + e];
             const uint32_t o = sw64(eslot[s0 + e], c16);
             uint4 w;
@@ -830,7 +833,7 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, c
       p.lna = c[0];
       p.lnw = c[1];
       p.nrc = nrc;
-      p.nb = std::min(kBuildWarps, na);
+      p.nb = std::min(kBuildWarps / 2, na);  // stage owners; two warps each
       p.nmma = std::min(p.nmma, na);  // every A/W stage belongs to exactly one issuer
       fit = true;
       break;

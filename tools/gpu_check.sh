@@ -12,9 +12,10 @@ timeout 420 python -m pytest tests -m gpu -q --timeout 90 --timeout-method threa
 rc=$?
 tail -40 gpurun_out/pytest_conv.txt
 timeout 200 python tools/conv_micro.py --shapes 32x32,64x64,6x32 --iters 5 > gpurun_out/micro_fp32.json 2> gpurun_out/micro_fp32.err
-
-cat gpurun_out/micro_fp32.json gpurun_out/micro_bf16.json
 timeout 200 python tools/conv_micro.py --shapes 32x32,64x64 --precision bf16 --iters 5 > gpurun_out/micro_bf16.json 2> gpurun_out/micro_bf16.err
-cat gpurun_out/micro_bf16.json
-tail -3 gpurun_out/micro_fp32.err
+timeout 200 python tools/conv_micro.py --shapes 64x64,96x96 --level 2 --iters 5 > gpurun_out/micro_fp32_l2.json 2> gpurun_out/micro_l2.err
+timeout 200 python tools/conv_micro.py --shapes 96x96,128x128 --level 3 --iters 5 > gpurun_out/micro_fp32_l3.json 2> gpurun_out/micro_l3.err
+cat gpurun_out/micro_fp32.json gpurun_out/micro_bf16.json gpurun_out/micro_fp32_l2.json gpurun_out/micro_fp32_l3.json
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -c 2200 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 exit $rc
