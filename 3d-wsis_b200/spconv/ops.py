@@ -52,9 +52,46 @@ def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padd
         rb = W.rulebook_subm(indices, spatial_shape, ksize, dilation, batch_size)
     else:
         rb, _ = W.rulebook_conv(indices, spatial_shape, ksize, stride, padding, dilation, batch_size)
+    if _LAZY_PAIRS:
+        lazy = LazyPairs(rb)
+        return rb.out_coords, lazy, lazy
     pairs, num = rb.pairs()
     pairs._wsis_rulebook = rb
     return rb.out_coords, pairs, num
+
+
+# The reference-format (indice_pairs, indice_pair_num) tensors exist only because indice_dict stores them
+# (conv.py:152); no kernel of this package reads them.  Inside `with lazy_pairs():` (wsis_b200.pipeline: the fused
+# inference path, where nothing looks into indice_dict) get_indice_pairs returns a LazyPairs handle instead and the
+# [K, 2, N] tensor (117 MB at the first U-Net level of a 4-scene batch) is only written if somebody asks for it.
+_LAZY_PAIRS = False
+
+
+class LazyPairs(object):
+    def __init__(self, rb):
+        self._wsis_rulebook = rb
+
+    def tensors(self):
+        return self._wsis_rulebook.pairs()
+
+    @property
+    def shape(self):
+        rb = self._wsis_rulebook
+        return torch.Size((rb.K, 2, rb.n_in))
+
+    def to(self, *_a, **_k):
+        return self
+
+
+class lazy_pairs(object):
+    def __enter__(self):
+        global _LAZY_PAIRS
+        self._old, _LAZY_PAIRS = _LAZY_PAIRS, True
+
+    def __exit__(self, *exc):
+        global _LAZY_PAIRS
+        _LAZY_PAIRS = self._old
+        return False
 
 
 def _rulebook_of(indice_pairs, indice_pair_num, n_in, n_out, subm):

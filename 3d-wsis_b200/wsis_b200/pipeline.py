@@ -61,7 +61,11 @@ def forward_batch(model, dbatch, use_coords=True, mode=4):
     extra = {"superpoint": superpoint, "GIs": [GraphInfo(dbatch["ecc_edge_index"], dbatch["ecc_edgefeats"])],
              "edge_u_list": dbatch["edge_u_list"], "edge_v_list": dbatch["edge_v_list"],
              "superpoint_cenetr_xyz": centers, "sp_index": sp_index, "edge_index_u": eindex, "num_superpoints": S}
-    ret = model(input_, p2v_map, extra)
+    if torch.is_grad_enabled() or model.training:
+        ret = model(input_, p2v_map, extra)
+    else:
+        with spconv.ops.lazy_pairs():  # inference: nothing reads the reference-format pair tensors
+            ret = model(input_, p2v_map, extra)
     aux = {"voxel_locs": voxel_locs, "p2v_map": p2v_map, "v2p_map": v2p_map, "centers": centers, "input": input_,
            "edge_index_u": eindex}
     return ret, aux
