@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t pad = ((raw + 1023u) & ~1023u) - raw;
   uint8_t *sm = smem_raw + pad;
   const int KB = p.KB;
-  const uint32_t na = 1u << p.lna, nw = 1u << p.lnw;
+  const uint32_t na = 1u << p.lna;  // pipeline stages: A operand block(s) + the unit's weight block(s), one barrier pair
   constexpr uint32_t a_stage = NS * kABlockBytes;
   const uint32_t b_block = (uint32_t)p.Cout * 64u;
   const uint32_t w_stage = NS * b_block;
@@ -285,8 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t rec_buf = rec_main + kRcap * 4;  // entry record + the first kRcap unique rows
   const uint32_t hdr_bytes = (uint32_t)rec_hdr_bytes(p.K);
   uint8_t *s_a = sm;                                  // [na][NS][128 x 64 B swizzled]  A operands
-  uint8_t *s_w = s_a + (size_t)na * a_stage;          // [nw][NS][Cout x 64 B swizzled] weight blocks (bulk copies)
-  uint8_t *s_rc = s_w + (size_t)nw * w_stage;         // [nrc][kRcap][row_b]            converted source rows
+  uint8_t *s_w = s_a + (size_t)na * a_stage;          // [na][NS][Cout x 64 B swizzled] weight blocks (bulk copies)
+  uint8_t *s_rc = s_w + (size_t)na * w_stage;         // [nrc][kRcap][row_b]            converted source rows
   uint8_t *s_rec = s_rc + (size_t)p.nrc * rc_buf;     // [p.nrec][rec_buf]               tile records (bulk copies)
   float *s_scale = reinterpret_cast<float *>(s_rec + (size_t)p.nrec * rec_buf);
   float *s_shift = s_scale + KB * kKB;
@@ -295,9 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t bar0 = smem_u32(bars);
   auto afull_bar = [&](uint32_t s) { return bar0 + 8u * s; };
   auto aempty_bar = [&](uint32_t s) { return bar0 + 8u * (na + s); };
-  auto wfull_bar = [&](uint32_t s) { return bar0 + 8u * (2 * na + s); };
-  auto wempty_bar = [&](uint32_t s) { return bar0 + 8u * (2 * na + nw + s); };
-  const uint32_t bar1 = bar0 + 8u * (2 * na + 2 * nw);
+  const uint32_t bar1 = bar0 + 8u * (2 * na);
   auto rcf_bar = [&](uint32_t s) { return bar1 + 8u * s; };
   auto rce_bar = [&](uint32_t s) { return bar1 + 8u * (p.nrc + s); };
   const uint32_t bar2 = bar1 + 8u * (2 * p.nrc);
@@ -305,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   auto rece_bar = [&](uint32_t s) { return bar2 + 8u * (p.nrec + s); };
   auto accf_bar = [&](uint32_t s) { return bar2 + 8u * (2 * p.nrec + s); };
   auto acce_bar = [&](uint32_t s) { return bar2 + 8u * (2 * p.nrec + 2 + s); };
-  const uint32_t nbars = 2 * na + 2 * nw + 2 * p.nrc + 2 * p.nrec + 4;
+  const uint32_t nbars = 2 * na + 2 * p.nrc + 2 * p.nrec + 4;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + nbars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -316,12 +314,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   }
   if (tid == 0) {
     for (uint32_t s = 0; s < na; ++s) {
-      mbar_init(afull_bar(s), 2);   // the two builder warps of the unit (each assembles half of its entries)
-      mbar_init(aempty_bar(s), 1);  // tcgen05.commit
-    }
-    for (uint32_t s = 0; s < nw; ++s) {
-      mbar_init(wfull_bar(s), 1);   // expect_tx arrive of the weight producer (+ the bulk copy's bytes)
-      mbar_init(wempty_bar(s), 1);  // tcgen05.commit
+      // full: the two builder warps of the unit (each assembles half of its entries) + the weight producer's
+      // expect_tx arrive (+ the bytes of its bulk copy); empty: ONE tcgen05.commit per unit releases the operand block
+      // and the weight block together (every tcgen05 instruction costs the issuing thread ~75 cycles, so the
+      // per-unit protocol is one wait, the MMAs and one commit)
+      mbar_init(afull_bar(s), 3);
+      mbar_init(aempty_bar(s), 1);
     }
     for (int s = 0; s < p.nrc; ++s) {
       mbar_init(rcf_bar(s), kGatherWarps);
@@ -609,13 +607,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         const uint32_t d0 = d_base + mi * p.Cout, d1 = per > 1 ? d0 + nmma * p.Cout : d0;
         for (uint32_t u = (mi - j0) & (nmma - 1); u < n; u += nmma) {
           const uint32_t j = j0 + u;
-          const uint32_t sa = j & (na - 1), sw = j & (nw - 1);
-          mbar_wait(afull_bar(sa), (j >> p.lna) & 1);
+          const uint32_t sa = j & (na - 1);
+          mbar_wait(afull_bar(sa), (j >> p.lna) & 1);  // operand rows (generic proxy, fenced by the builders) + weights
           if (lane == 0) tl_event(p, 16 + mi, itx, 0, u);
-          if (!WSIS_DBG(16)) mbar_wait(wfull_bar(sw), (j >> p.lnw) & 1);
-          tc_fence_after();
-          if (lane == 0) tl_event(p, 16 + mi, itx, 1, u);
-          const uint64_t ad = desc0 + ((a_base + sa * a_stage) >> 4), bd = desc0 + ((w_base + sw * w_stage) >> 4);
+          const uint64_t ad = desc0 + ((a_base + sa * a_stage) >> 4), bd = desc0 + ((w_base + sa * w_stage) >> 4);
           if (elect_one()) {
             const uint4 vm = lds128(m_base + sa * 16);  // valid-slot mask of the unit; the MMA takes its complement
             const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
@@ -632,8 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
                 mma_bf16(d1, ad + (kABlockBytes >> 4) + 2, bd + 2, idesc, off);
               }
             }
-            if WSIS_DBG(64) mbar_arrive(aempty_bar(sa)); else mma_commit(aempty_bar(sa));
-            if (!WSIS_DBG(16)) mma_commit(wempty_bar(sw));
+            mma_commit(aempty_bar(sa));
           }
           __syncwarp();
           if (lane == 0) tl_event(p, 16 + mi, itx, 2, u);
@@ -666,23 +660,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       __syncwarp();
     }
   } else {
-    // ===================== weight producer: bulk copy of each unit's pre-swizzled weight block, nw units ahead =====
+    // ===================== weight producer: bulk copy of each unit's pre-swizzled weight block into its stage ======
     uint32_t j = 0;
     const uint32_t w_base = smem_u32(s_w);
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles && !WSIS_DBG(16); tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const uint32_t mask = uni((uint32_t)__ldg(&p.meta[tile].z));
       for (int kb = 0; kb < KB; ++kb) {
         for (uint32_t mm = mask; mm; mm &= mm - 1, ++j) {
           const int k = __ffs(mm) - 1;
-          const uint32_t sw = j & (nw - 1);
-          mbar_wait(wempty_bar(sw), ((j >> p.lnw) & 1) ^ 1);
+          const uint32_t sw = j & (na - 1);
+          mbar_wait(aempty_bar(sw), ((j >> p.lna) & 1) ^ 1);
           if (lane == 0) tl_event(p, 24, 0, 0, j);
           if (elect_one()) {
             if WSIS_DBG(8) {
-              mbar_arrive(wfull_bar(sw));
+              mbar_arrive(afull_bar(sw));
             } else {
-              mbar_expect_tx(wfull_bar(sw), w_stage);
-              bulk_g2s(w_base + sw * w_stage, p.packed + (size_t)(k * KB + kb) * w_stage, w_stage, wfull_bar(sw));
+              mbar_expect_tx(afull_bar(sw), w_stage);
+              bulk_g2s(w_base + sw * w_stage, p.packed + (size_t)(k * KB + kb) * w_stage, w_stage, afull_bar(sw));
             }
           }
           __syncwarp();
@@ -817,7 +811,7 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, c
              "conv_umma: max_record_bytes %d must be a multiple of 16 in [0, %d]", max_record_bytes, rec_stride_bytes(K));
   p.rec_main = max_record_bytes ? max_record_bytes : rec_stride_bytes(K);
   const int64_t rc_buf = (int64_t)kRcap * NS * 64, rec_buf = p.rec_main + kRcap * 4;
-  static const int pref[][3] = {{3, 3, 3}, {3, 3, 2}, {3, 2, 2}, {2, 3, 3}, {2, 3, 2}, {2, 2, 2}, {1, 2, 2}, {1, 1, 2}, {1, 1, 1}};
+  static const int pref[][3] = {{3, 3, 3}, {3, 3, 2}, {2, 2, 3}, {2, 2, 2}, {1, 1, 2}, {1, 1, 1}, {0, 0, 1}};
   const int64_t budget = 227 * 1024;
   {
     const char *d = getenv("WSIS_CONV_NREC");
@@ -826,9 +820,9 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, c
   int64_t smem = 0;
   bool fit = false;
   for (auto &c : pref) {
-    const int na = 1 << c[0], nw = 1 << c[1], nrc = c[2];
-    const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nw + 2 * nrc + 2 * p.nrec + 4) * 8 + 64;
-    smem = misc + na * a_stage + nw * w_stage + nrc * rc_buf + p.nrec * rec_buf;
+    const int na = 1 << c[0], nrc = c[2];
+    const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nrc + 2 * p.nrec + 4) * 8 + 64;
+    smem = misc + na * (a_stage + w_stage) + nrc * rc_buf + p.nrec * rec_buf;
     if (smem <= budget) {
       p.lna = c[0];
       p.lnw = c[1];
