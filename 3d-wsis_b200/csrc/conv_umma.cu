@@ -559,15 +559,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
 #pragma unroll
           for (int i = 0; i < PF; ++i)
             if ((2 * i + half) * EPI + e_in < n && !WSIS_DBG(2)) sts128(abase + off[i], v[i]);
-          for (int e = (2 * PF + half) * EPI + e_in; e < n; e += 2 * EPI) {  // long units (dense neighbourhoods)
-            const uint32_t loc = eloc[s0 + e];
-            const uint32_t o = sw64(eslot[s0 + e], c16);
-            uint4 w;
-            if (loc < kRcap)
-              w = lds128(rcb + loc * row_b + ((NS == 2 ? (xl ^ ((loc & 1u) << 2)) : xl) << 4));
-            else
-              w = fetch_direct(p, tile, loc, kb * kKB + c16 * 8, part, s_scale, s_shift);
-            sts128(abase + o, w);
+          // long units (dense neighbourhoods, 50-128 entries): the same batches of PF loads then PF stores
+          for (int g0 = 2 * PF; g0 * EPI < n; g0 += 2 * PF) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+              const int e = (g0 + 2 * i + half) * EPI + e_in;
+              if (e < n) {
+                const uint32_t loc = eloc[s0 + e];
+                off[i] = sw64(eslot[s0 + e], c16);
+                if (loc < kRcap)
+                  v[i] = lds128(rcb + loc * row_b + ((NS == 2 ? (xl ^ ((loc & 1u) << 2)) : xl) << 4));
+                else
+                  v[i] = fetch_direct(p, tile, loc, kb * kKB + c16 * 8, part, s_scale, s_shift);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < PF; ++i)
+              if ((g0 + 2 * i + half) * EPI + e_in < n) sts128(abase + off[i], v[i]);
           }
           if (!WSIS_DBG(128)) fence_proxy_async();
           __syncwarp();
