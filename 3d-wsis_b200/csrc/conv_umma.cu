@@ -6,25 +6,28 @@
 //   dst[r,:] = residual[r,:] + sum_k  prologue(src[nbr[r,k],:]) . W[k]
 //
 // Work is organised in TILES of 128 output rows taken in a spatially sorted (Morton) order, built once per
-// coordinate set by tilemap.cu: `order[t*128+i]` is the output row of tile slot i and `pmap[t*128+i, k]` the
-// source row feeding it through kernel offset k (-1 = none).  A tile is a compact surface patch, so the rows
-// it gathers are shared by ~9 offsets and by the neighbouring tiles: the gather is served by L1/L2 and HBM
-// sees each feature row about once.
+// coordinate set by tilemap.cu: `order[t*128+i]` is the output row of tile slot i; the tile's RECORD lists, per
+// kernel offset k, the entries (tile slot, index into the tile's list of DISTINCT source rows).  A tile is a
+// compact surface patch: ~160-230 distinct rows feed its ~480-1400 entries, and neighbouring tiles share their
+// halos through L2, so HBM sees each feature row about once (ncu: DRAM bytes <= algorithmic bytes).
 //
-// One persistent CTA per SM; a CTA owns tiles (= the 128 TMEM lanes of one accumulator):
-//   warps 0-3   epilogue : tcgen05.ld accumulator -> registers -> (+residual) -> global, once per tile
-//   warps 4-11  loaders  : find the kernel offsets that have any neighbour in the tile (the others cost
-//                          nothing), gather the fp32 source rows with 16-byte loads kept DEPTH units in
-//                          flight, apply the fused eval-BatchNorm+ReLU prologue, split fp32 -> bf16 hi (+ bf16
-//                          mid for the 1e-4 path) and store them in the 64B-swizzled K-major layout the UMMA
-//                          descriptors expect; one elected loader also issues the cp.async.bulk (1-D TMA) of
-//                          the unit's pre-swizzled weight block
-//   warp 12     MMA      : one elected thread issues tcgen05.mma (M=128, N=Cout, K=16) into TMEM
-//   warp 13     map      : cp.async.bulk of the next tile's neighbour-map slice (double buffered)
-// The pipeline unit is (active kernel offset k, 32-channel block kb); units flow through an NSTAGE mbarrier
-// ring (full: loaders + bulk-copy tx bytes -> MMA; empty: tcgen05.commit -> loaders).  The accumulator is
-// double buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
-// There is no scatter and there are no atomics: every output row is written exactly once.
+// One persistent CTA per SM; a CTA owns tiles (= the 128 TMEM lanes of one accumulator).  640 threads:
+//   warps 0-3    epilogue  : tcgen05.ld accumulator -> registers -> (+residual) -> global, once per tile
+//   warps 4-7    gatherers : fetch every distinct source row of the tile ONCE per 32-channel block (16-byte loads,
+//                            8 in flight per lane), fused eval-BatchNorm+ReLU prologue, fp32 -> bf16 hi (+ bf16
+//                            mid for the 1e-4 path), park the rows in a shared-memory ROW CACHE (nrc buffers)
+//   warps 8-15   builders  : two warps per pipeline unit (active offset k, 32-channel block kb): copy the unit's
+//                            entries row cache -> 64B-swizzled K-major A block (shared -> shared); rows are
+//                            prefetched into registers before the stage-free wait
+//   warps 16-17  issuers   : warp-uniform loop, one elect.sync lane issues tcgen05.mma (M=128, N=Cout, K=16) with
+//                            the unit's disable-output-lane mask, then one tcgen05.commit per unit
+//   warp 18      records   : cp.async.bulk of the next tile's record (+ its first kRcap unique rows)
+//   warp 19      weights   : cp.async.bulk of each unit's pre-swizzled weight block into the unit's stage
+// Units flow through a ring of 2^lna stages {A block(s), weight block(s)} with one barrier pair per stage
+// (full: 2 builder arrives + the weight copy's expect_tx and bytes; empty: tcgen05.commit).  The accumulator is
+// double buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1; each issuer has its own
+// accumulator (summed by the epilogue).  There is no scatter and there are no atomics: every output row is
+// written exactly once.  DESIGN.md 4 has the measured cost model and what bounds the kernel today.
 //
 // Precision: precision==1 uses bf16 operands (fp32 accumulate).  precision==3 splits both operands into
 // bf16 hi + bf16 mid and issues hi.hi + hi.mid + mid.hi (error ~2^-17 per product, fp32 accumulate in TMEM)
