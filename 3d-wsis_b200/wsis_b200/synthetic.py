@@ -108,6 +108,13 @@ def make_scene(seed, n_points=150000, room=(8.0, 6.0, 2.6), n_boxes=12, sp_cell=
                 sp_class=sp_cls, sp_instance=sp_inst, seed_label=seed_label, num_superpoints=S)
 
 
+def make_room_s3dis(seed, n_points=1000000):
+    """S3DIS-shaped room (BASELINE.json configs[3]): 20 m x 15 m x 3 m, 1 M points, 5 cm voxels
+    (scale 20), ~10k superpoints (0.4 m patches), 40 boxes."""
+    return make_scene(seed, n_points=n_points, room=(20.0, 15.0, 3.0), n_boxes=40, sp_cell=0.4, scale=20,
+                      box_scale=1.5)
+
+
 def make_shell(n_floor=(400, 300), wall=(400, 75)):
     """The reproducible 150 000-voxel micro-shape of SURVEY.md §6: a 400x300 floor plus a 400x75 wall, one
     voxel per cell (spatial_shape [400,300,128])."""

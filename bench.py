@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=4, help="scenes per batch (configs[1]: 4)")
     ap.add_argument("--points", type=int, default=150000, help="points per scene")
+    ap.add_argument("--shape", default="scannet", choices=["scannet", "s3dis"],
+                    help="scannet: configs[1] (8x6x2.6 m rooms, 2 cm voxels); s3dis: configs[3] (20x15x3 m rooms, 5 cm "
+                         "voxels; use --points 1000000 --scenes 1)")
     ap.add_argument("--precision", default=os.environ.get("WSIS_PRECISION", "fp32"), choices=["fp32", "bf16", "simt"])
     ap.add_argument("--cpu-sample-scenes", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -58,9 +61,14 @@ def parse():
 
 
 def workload_config(args, extra=None):
-    cfg = {"workload": "ScanNet_v2_3D_WSIS inference, batch of %d synthetic ScanNet-shaped scenes "
-                       "(%d pts/scene, 2 cm voxels, ~3k superpoints/scene), UNet+pooling+ECC+affinity forward"
-                       % (args.scenes, args.points),
+    if args.shape == "s3dis":
+        what = ("S3DIS_Area5_3D_WSIS inference, batch of %d synthetic S3DIS-shaped rooms (%d pts/room, 20x15x3 m, 5 cm "
+                "voxels, ~10k superpoints/room), UNet+pooling+ECC+affinity forward" % (args.scenes, args.points))
+    else:
+        what = ("ScanNet_v2_3D_WSIS inference, batch of %d synthetic ScanNet-shaped scenes "
+                "(%d pts/scene, 2 cm voxels, ~3k superpoints/scene), UNet+pooling+ECC+affinity forward"
+                % (args.scenes, args.points))
+    cfg = {"workload": what,
            "scenes_per_step": args.scenes, "points_per_scene": args.points, "weights": "random-init, seed 123",
            "l2": "flushed between timed steps (256 MiB write)"}
     cfg.update(extra or {})
@@ -71,7 +79,8 @@ def make_batches(args, rank, n_batches):
     from wsis_b200 import synthetic
     out = []
     for b in range(n_batches):
-        scenes = [synthetic.make_scene(2000 + 100 * rank + 10 * b + i, n_points=args.points) for i in range(args.scenes)]
+        mk = synthetic.make_room_s3dis if args.shape == "s3dis" else synthetic.make_scene
+        scenes = [mk(2000 + 100 * rank + 10 * b + i, n_points=args.points) for i in range(args.scenes)]
         out.append(synthetic.collate(scenes))
     return out
 
@@ -147,7 +156,8 @@ def cpu_pass(args, n_steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     net = pipeline.build_network(seed=123, device="cpu").eval()
-    scenes = [synthetic.make_scene(2000 + i, n_points=args.points) for i in range(args.cpu_sample_scenes)]
+    mk = synthetic.make_room_s3dis if args.shape == "s3dis" else synthetic.make_scene
+    scenes = [mk(2000 + i, n_points=args.points) for i in range(args.cpu_sample_scenes)]
     batch = synthetic.collate(scenes)
     times, stages, kind = [], None, "port"
     for it in range(warmup + n_steps):

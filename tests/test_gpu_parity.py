@@ -659,3 +659,49 @@ def test_conv_row_cache_overflow_and_narrow_rows(W, cin, cout, prec, tol):
         exp[ok] += g[m[ok, k]] @ w[k].astype(np.float64)
     out = W.sparse_conv(cu(f), cu(w), cu(m), n, 0, prologue=(cu(scale), cu(shift), 1), precision=prec).cpu().numpy()
     assert rel(out, exp) < tol
+
+
+def test_s3dis_shaped_room_full_size_properties(W):
+    """BASELINE.json configs[3]: one S3DIS-shaped room (1 M points, 5 cm voxels, ~6k superpoints) through the whole
+    hot path.  At this size the CPU oracle is replaced by size-independent properties: voxelization is a partition of
+    the points, the submanifold rulebook is symmetric, the tensor-core conv agrees with the exact-fp32 kernel and is
+    linear, superpoint pooling agrees with an index_add formulation, and the network outputs are finite."""
+    import pointgroup_ops
+    from wsis_b200 import pipeline, synthetic
+    room = synthetic.make_room_s3dis(7, n_points=1000000)
+    batch = synthetic.collate([room])
+    dbatch, _ = pipeline.to_device(batch)
+    n = batch["locs"].shape[0]
+    locs, p2v, v2p = pointgroup_ops.voxelization_idx(dbatch["locs"], 1, 4)
+    m = locs.shape[0]
+    assert m == len(np.unique(room["locs"], axis=0))
+    assert int(v2p[:, 0].sum()) == n and int(p2v.max()) == m - 1
+    assert torch.equal(locs[p2v.long()], dbatch["locs"])                   # every point lies in the voxel it maps to
+    rb = W.rulebook_subm(locs.int(), batch["spatial_shape"], 3, 1, batch_size=1)
+    valid = (rb.nbr_in >= 0)
+    num = valid.sum(0).cpu().numpy()
+    assert num[13] == m and np.array_equal(num, num[::-1])
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand((m, 32), device="cuda", generator=g) - 0.5
+    y = torch.rand((m, 32), device="cuda", generator=g) - 0.5
+    w = (torch.rand((27, 32, 32), device="cuda", generator=g) - 0.5) * 0.3
+    tiles = rb.tiles_out()
+    fx = W.sparse_conv(x, w, rb.nbr_in, m, 1, precision="fp32", tiles=tiles)
+    exact = W.sparse_conv(x, w, rb.nbr_in, m, 1, precision="simt")
+    scale = float(exact.abs().max())
+    assert float((fx - exact).abs().max()) < FP32_TOL * scale
+    fy = W.sparse_conv(y, w, rb.nbr_in, m, 1, precision="fp32", tiles=tiles)
+    fxy = W.sparse_conv(2.0 * x - y, w, rb.nbr_in, m, 1, precision="fp32", tiles=tiles)
+    assert float((fxy - (2.0 * fx - fy)).abs().max()) < 2e-4 * scale
+    sp = dbatch["superpoint"]
+    S = batch["num_superpoints"]
+    pts = torch.rand((n, 32), device="cuda", generator=g)
+    pooled = W.segment_reduce(pts, W.SegmentIndex(sp, S), "mean")
+    ref = torch.zeros((S, 32), device="cuda").index_add_(0, sp, pts) / torch.bincount(sp, minlength=S).clamp(min=1)[:, None]
+    assert float((pooled - ref).abs().max()) < 1e-5
+    net = pipeline.build_network(seed=123, device="cuda").eval()
+    with torch.no_grad():
+        ret, _ = pipeline.forward_batch(net, dbatch)
+    assert ret["semantic_scores"].shape == (n, 20) and ret["edge_affinity"].shape[0] == batch["edge_u_list"].shape[0]
+    for k, v in ret.items():
+        assert bool(torch.isfinite(v).all()), k
