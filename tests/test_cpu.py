@@ -444,3 +444,64 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "scenes/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# instance clustering: identical masks against the reference's own function
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cluster_scene0", "cluster_scene1"])
+def test_clustering_matches_reference_golden(name):
+    """tests/golden/make_golden_cluster.py ran the reference's clustering_in_graph (test_scannetv2.py:281-455) on
+    these inputs; the aggregate-based implementation must give the same instances: identical masks and labels, and
+    the same confidences."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_cluster as mg
+    from wsis_b200 import cluster
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    case, nbrs = mg.make_case(int(gold["seed"]), int(gold["n_points"]))
+    for k in ("sem", "off", "occ", "size"):                      # the stored inputs are the ones the reference saw
+        assert np.array_equal(case[k], gold[k]), k
+    conf, label, masks = cluster.clustering_in_graph(case["xyz"], case["superpoint"], nbrs, case["sem"], case["off"],
+                                                     case["occ"], case["size"])
+    assert masks.shape[1] == len(case["xyz"]) and masks.dtype == int
+    assert np.array_equal(np.packbits(masks.astype(bool), axis=1), gold["masks"])
+    assert np.array_equal(label, gold["label_id"])
+    assert np.allclose(conf, gold["conf"], rtol=0, atol=0)
+    assert masks.sum(0).max() <= 1                               # instances are disjoint
+
+
+def test_clustering_fragments_and_edge_cases():
+    """Two same-class boxes far apart stay two instances; a tiny same-class group whose voxel count is below 0.3 x
+    the predicted occupancy is a fragment and is absorbed by the nearest primary of its class when it is within the
+    primary's radius; classes outside the instance label set never form instances."""
+    from wsis_b200 import cluster
+    rng = np.random.default_rng(5)
+    pts, sp = [], []
+
+    def blob(center, n, sid):
+        pts.append(center + rng.uniform(-0.2, 0.2, (n, 3)))
+        sp.append(np.full(n, sid))
+
+    blob(np.array([0.0, 0, 0]), 400, 0)
+    blob(np.array([0.3, 0, 0]), 400, 1)        # same object as 0
+    blob(np.array([5.0, 0, 0]), 400, 2)        # second object, same class
+    blob(np.array([0.6, 0, 0]), 3, 3)          # fragment next to object A (3 points)
+    blob(np.array([9.0, 9, 0]), 300, 4)        # floor class: not an instance class
+    xyz = np.concatenate(pts).astype(np.float32)
+    sp = np.concatenate(sp)
+    nbrs = cluster.neighbors_from_edges(np.array([[0, 1], [1, 3], [2, 4]]), 5)
+    sem = np.array([4, 4, 4, 4, 1])            # semantic_ind2label[1] = 2 -> not in the instance label set
+    off = np.zeros((5, 3), np.float32)
+    off[1] = [-0.3, 0, 0]                      # superpoint 1 votes for the centre of superpoint 0
+    off[3] = [-0.1, 0, 0]                      # the fragment's centre stays 0.5 m from A's: not BFS-merged (0.25*1.2)
+    occ = np.log(np.array([400.0, 400, 400, 400, 300])).astype(np.float32)
+    size = np.full(5, 1.2, np.float32)
+    conf, label, masks = cluster.clustering_in_graph(xyz, sp, nbrs, sem, off, occ, size)
+    assert len(conf) == 2 and list(label) == [5, 5]              # semantic_ind2label[4]
+    a, b = masks[0].astype(bool), masks[1].astype(bool)
+    assert set(np.unique(sp[a])) == {0, 1, 3} and set(np.unique(sp[b])) == {2}   # the fragment was absorbed by A
+    assert not masks[:, sp == 4].any()
+    # without any primary instance the reference would index an empty list; here the result is simply empty
+    conf, label, masks = cluster.clustering_in_graph(xyz, sp, nbrs, np.array([1, 1, 1, 1, 1]), off, occ, size)
+    assert len(conf) == 0 and masks.shape == (0, len(xyz))
