@@ -17,6 +17,7 @@ _SCALARS = {
     "int": ctypes.c_int,
     "int32_t": ctypes.c_int32,
     "int64_t": ctypes.c_int64,
+    "float": ctypes.c_float,
     "wsis_stream_t": ctypes.c_void_p,
 }
 

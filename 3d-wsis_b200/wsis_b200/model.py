@@ -231,6 +231,18 @@ class RNNGraphConvModule(nn.Module):
         weights = self._fnet(edgefeats)
         nc = hx.size(1)
         assert hx.dim() == 2 and weights.dim() == 2 and weights.size(1) == nc * nc
+        cell = self._cell
+        if (not torch.is_grad_enabled() and hx.is_cuda and hx.dtype == torch.float32 and nc == 32
+                and isinstance(cell, GRUCellEx) and cell._ingate and cell.bias):
+            # inference: one kernel per GRU step (message, gates, layer norms and the concatenation fused;
+            # csrc/ecc.cu) instead of ~20 torch launches
+            key = tuple(p._version for p in cell.parameters()) + tuple(p.data_ptr() for p in cell.parameters())
+            if getattr(self, "_packed_key", None) != key:
+                self._packed_key, self._packed = key, W.pack_ecc_gru(cell)
+            tseg = W.SegmentIndex(edge_index[1], hx.shape[0])
+            return W.ecc_gru(hx, weights, edge_index[0], tseg, self._packed, self._nrepeats,
+                             layernorm=cell._layernorm, eps=cell._modules['ini'].eps if cell._layernorm else 1e-5,
+                             cat_all=self._cat_all)
         hxs = [hx]
         for _ in range(self._nrepeats):
             hx = self._cell(self.nn(hx, edge_index, weights), hx)

@@ -507,6 +507,40 @@ def edge_attention(q, k, v, ecc, centers, edge_u, edge_v, eseg, pos_mlp):
     return aff, sp
 
 
+def pack_ecc_gru(cell):
+    """GRUCellEx parameters -> float[wsis_ecc_gru_param_floats()] in the kernel's (transposed) layout."""
+    ig = cell._modules["ig"]
+    buf = torch.cat([ig.weight.detach().t().reshape(-1), ig.bias.detach().reshape(-1),
+                     cell.weight_ih.detach().t().reshape(-1), cell.weight_hh.detach().t().reshape(-1),
+                     cell.bias_ih.detach().reshape(-1), cell.bias_hh.detach().reshape(-1)]).float().contiguous()
+    assert buf.numel() == lib().value("wsis_ecc_gru_param_floats")
+    return buf
+
+
+def ecc_gru(hx, filters, src, tseg, params, nrepeats, layernorm=True, eps=1e-5, cat_all=True):
+    """`nrepeats` steps of the edge-conditioned GRU (spg_modules.py:152-185, 226-253), one kernel per step.
+    hx f32[S,32]; filters f32[E,1024]; src int64[E]; tseg = SegmentIndex of the edge TARGETS."""
+    hx = _cuda(hx, "hx").contiguous()
+    filters = _cuda(filters, "filters").contiguous()
+    src = src.contiguous()
+    S, F = hx.shape
+    if F != 32 or hx.dtype != torch.float32 or filters.dtype != torch.float32 or filters.shape[1] != F * F:
+        raise RuntimeError("wsis_b200: ecc_gru needs float32 nfeat=32 states and [E,1024] filters")
+    assert src.dtype == torch.int64 and tseg.S == S and tseg.n == src.shape[0] == filters.shape[0]
+    width = F * (nrepeats + 1)
+    cat = torch.empty((S, width), dtype=torch.float32, device=hx.device) if cat_all else None
+    if cat_all:
+        cat[:, :F] = hx
+    h = hx
+    for r in range(nrepeats):
+        out = torch.empty_like(h)
+        cat_ptr = ctypes.c_void_p(cat.data_ptr() + 4 * F * (r + 1)) if cat_all else None
+        lib().call("wsis_ecc_gru_step", _ptr(h), _ptr(filters), _ptr(src), _ptr(tseg.order), _ptr(tseg.offsets), S,
+                   _ptr(params), int(layernorm), float(eps), _ptr(out), cat_ptr, width, _stream())
+        h = out
+    return cat if cat_all else h
+
+
 def pack_pos_mlp(fc_position):
     """fc_position = Sequential(Linear(3,16), ReLU, Linear(16,1)) (backbone_3D_WSIS.py:110-114) -> f32[81]."""
     l1, l2 = fc_position[0], fc_position[2]

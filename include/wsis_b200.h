@@ -226,6 +226,21 @@ int wsis_edge_attention(const float *q, const float *k, const float *v, const fl
                         const int32_t *eoffsets, int64_t S, int64_t E, int D, const float *pos_mlp,
                         float *affinity, float *sp_feat, wsis_stream_t stream);
 
+/* One step of the edge-conditioned GRU (ECC-GRU: modules/model/spg_modules.py:152-185 NNConv with mean aggregation,
+ * :226-253 GRUCellEx with input gate and un-affine layer norms), nfeat = 32, one warp per target superpoint:
+ *   m[t] = mean_{j in [offsets[t], offsets[t+1])} h[src[e]]^T . filters[e], e = eorder[j]  (filters float[E, 32*32],
+ *          [in][out]; eorder = NULL means e = j)
+ *   h_out[t] = GRUCellEx(m[t], h[t]);  cat_out[t*cat_stride + 0..31] = h_out[t] when cat_out != NULL.
+ * (eorder int32[E], offsets int32[S+1]) = CSR of the edges over their TARGET superpoint (wsis_segment_csr on
+ * edge_index[1]); src int64[E] = edge_index[0].  params float[wsis_ecc_gru_param_floats()] =
+ *   ig.weight^T [32][32] | ig.bias [32] | weight_ih^T [32][96] | weight_hh^T [32][96] | bias_ih [96] | bias_hh [96].
+ * h and h_out must be different buffers. */
+int64_t wsis_ecc_gru_param_floats(void);
+int wsis_ecc_gru_step(const float *h, const float *filters, const int64_t *src, const int32_t *eorder,
+                      const int32_t *offsets, int64_t S,
+                      const float *params, int layernorm, float eps, float *h_out, float *cat_out, int64_t cat_stride,
+                      wsis_stream_t stream);
+
 /* Random-walk label propagation (modules/datasets/scannetv2_dataset.py:664-735 + the dense fill at
  * train_scannetv2.py:565-570), float64 like the reference, exploiting that the transition matrix is
  * adjacency-masked and that only seed rows of T^(it+1) are read (:714-715).

@@ -705,3 +705,28 @@ def test_s3dis_shaped_room_full_size_properties(W):
     assert ret["semantic_scores"].shape == (n, 20) and ret["edge_affinity"].shape[0] == batch["edge_u_list"].shape[0]
     for k, v in ret.items():
         assert bool(torch.isfinite(v).all()), k
+
+
+@pytest.mark.parametrize("S,E,layernorm", [(700, 6000, True), (50, 40, True), (300, 2500, False), (33, 1, True)])
+def test_ecc_gru_fused_matches_module(W, S, E, layernorm):
+    """csrc/ecc.cu (one kernel per GRU step) against the module-by-module torch formulation of
+    spg_modules.py:152-185 / 226-253 (NNConv mean aggregation + GRUCellEx), which the golden network test pins to the
+    reference.  Includes superpoints without in-edges, unsorted targets and duplicate edges."""
+    from wsis_b200 import model as M
+    torch.manual_seed(S + E)
+    rng = np.random.default_rng(S * 7 + E)
+    fnet = M.create_fnet([13, 32, 128, 64, 32 * 32], True, True, 2)
+    cell = M.GRUCellEx(32, 32, bias=True, layernorm=layernorm, ingate=True)
+    mod = M.RNNGraphConvModule(cell, fnet, 32, nrepeats=7, cat_all=True).cuda().eval()
+    src = rng.integers(0, S, E)
+    tgt = rng.integers(0, max(S - 3, 1), E)                    # the last superpoints never receive a message
+    edge_index = cu(np.stack([src, tgt]).astype(np.int64).reshape(2, E))
+    feats = cu(rng.standard_normal((E, 13)).astype(np.float32))
+    mod.set_info(M.GraphInfo(edge_index, feats))
+    hx = cu(rng.standard_normal((S, 32)).astype(np.float32))
+    ref = mod(hx).detach()                                      # grad mode: the torch formulation
+    with torch.no_grad():
+        out = mod(hx)                                           # inference: the fused kernel
+    assert out.shape == ref.shape == (S, 32 * 8)
+    assert torch.equal(out[:, :32], hx)
+    assert rel(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5
