@@ -734,6 +734,55 @@ __global__ void pack_weights_kernel(const float *__restrict__ W, int K, int Cin,
 using namespace wsis;
 using namespace wsis::umma;
 
+// Launch plan of a layer shape: TMEM accumulators / issuers and the largest pipeline (stages, row-cache buffers) that
+// fits the 227 KB of dynamic shared memory.  Pure host arithmetic (also exported as wsis_conv_umma_plan so that the
+// CPU test suite can check that every layer shape of the model has a plan).
+static int plan_launch(wsis::umma::Params &p, int K, int Cin, int Cout, int NS, int max_record_bytes, int64_t *smem_out) {
+  using namespace wsis::umma;
+  p.KB = (Cin + kKB - 1) / kKB;
+  // one accumulate chain (TMEM accumulator) per issuer, as far as the 512 TMEM columns allow
+  int nacc = kMmaWarps;
+  while (nacc > 1 && 2 * nacc * Cout > 512) nacc >>= 1;
+  p.nacc = nacc;
+  p.nmma = std::min(nacc, kMmaWarps);  // one accumulate chain per issuer (two when nacc > nmma)
+  int cols = 32;
+  while (cols < 2 * nacc * Cout) cols <<= 1;
+  p.tmem_cols = cols;
+  // shared memory: A ring (2^lna stages), weight ring (2^lnw), row cache (nrc buffers), records; shrink the rings
+  // in this order of preference until the layer fits
+  const int64_t a_stage = (int64_t)NS * kABlockBytes, w_stage = (int64_t)NS * Cout * 64;
+  // the record buffers are sized for the largest record of THIS tile map when the caller knows it (0 = worst case)
+  WSIS_CHECK(max_record_bytes >= 0 && max_record_bytes % 16 == 0 && max_record_bytes <= rec_stride_bytes(K),
+             "conv_umma: max_record_bytes %d must be a multiple of 16 in [0, %d]", max_record_bytes, rec_stride_bytes(K));
+  p.rec_main = max_record_bytes ? max_record_bytes : rec_stride_bytes(K);
+  const int64_t rc_buf = (int64_t)kRcap * NS * 64, rec_buf = p.rec_main + kRcap * 4;
+  static const int pref[][3] = {{3, 3, 3}, {3, 3, 2}, {2, 2, 3}, {2, 2, 2}, {1, 1, 2}, {1, 1, 1}, {0, 0, 1}};
+  const int64_t budget = 227 * 1024;
+  {
+    const char *d = getenv("WSIS_CONV_NREC");
+    p.nrec = d ? std::max(2, std::min(kMaxRec, atoi(d))) : 2;
+  }
+  int64_t smem = 0;
+  bool fit = false;
+  for (auto &c : pref) {
+    const int na = 1 << c[0], nrc = c[2];
+    const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nrc + 2 * p.nrec + 4) * 8 + 64;
+    smem = misc + na * (a_stage + w_stage) + nrc * rc_buf + p.nrec * rec_buf;
+    if (smem <= budget) {
+      p.lna = c[0];
+      p.lnw = c[1];
+      p.nrc = nrc;
+      p.nb = std::min(kBuildWarps / 2, na);  // stage owners; two warps each
+      p.nmma = std::min(p.nmma, na);  // every A/W stage belongs to exactly one issuer
+      fit = true;
+      break;
+    }
+  }
+  WSIS_CHECK(fit, "conv_umma: shared memory budget exceeded for Cin=%d Cout=%d K=%d", Cin, Cout, K);
+  *smem_out = smem;
+  return 0;
+}
+
 static unsigned long long *g_tl = nullptr;
 static int g_tl_cap = 0;
 
@@ -764,6 +813,18 @@ int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpo
   pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(W, K, Cin, Cout, transpose_w, precision == 3 ? 2 : 1,
                                                              (uint8_t *)packed);
   WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_conv_umma_plan(int K, int Cin, int Cout, int precision, int max_record_bytes, int32_t *plan) {
+  WSIS_CHECK(wsis_conv_umma_supported(Cin, Cout), "conv_umma_plan: unsupported Cin=%d Cout=%d", Cin, Cout);
+  WSIS_CHECK(K >= 1 && K <= 32, "conv_umma_plan: kernel volume %d not in [1,32]", K);
+  WSIS_CHECK(precision == 1 || precision == 3, "conv_umma_plan: precision must be 1 or 3");
+  Params p;
+  int64_t smem = 0;
+  if (plan_launch(p, K, Cin, Cout, precision == 3 ? 2 : 1, max_record_bytes, &smem)) return 1;
+  const int out[8] = {(int)smem, 1 << p.lna, p.nrc, p.nrec, p.nb, p.nacc, p.nmma, p.tmem_cols};
+  for (int i = 0; i < 8; ++i) plan[i] = out[i];
   return 0;
 }
 
@@ -806,45 +867,8 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, c
     const char *d = getenv("WSIS_CONV_DEBUG");
     p.dbg = d ? atoi(d) : 0;
   }
-  // one accumulate chain (TMEM accumulator) per issuer, as far as the 512 TMEM columns allow
-  int nacc = kMmaWarps;
-  while (nacc > 1 && 2 * nacc * Cout > 512) nacc >>= 1;
-  p.nacc = nacc;
-  p.nmma = std::min(nacc, kMmaWarps);  // one accumulate chain per issuer (two when nacc > nmma)
-  int cols = 32;
-  while (cols < 2 * nacc * Cout) cols <<= 1;
-  p.tmem_cols = cols;
-  // shared memory: A ring (2^lna stages), weight ring (2^lnw), row cache (nrc buffers), records; shrink the rings
-  // in this order of preference until the layer fits
-  const int64_t a_stage = (int64_t)NS * kABlockBytes, w_stage = (int64_t)NS * Cout * 64;
-  // the record buffers are sized for the largest record of THIS tile map when the caller knows it (0 = worst case)
-  WSIS_CHECK(max_record_bytes >= 0 && max_record_bytes % 16 == 0 && max_record_bytes <= rec_stride_bytes(K),
-             "conv_umma: max_record_bytes %d must be a multiple of 16 in [0, %d]", max_record_bytes, rec_stride_bytes(K));
-  p.rec_main = max_record_bytes ? max_record_bytes : rec_stride_bytes(K);
-  const int64_t rc_buf = (int64_t)kRcap * NS * 64, rec_buf = p.rec_main + kRcap * 4;
-  static const int pref[][3] = {{3, 3, 3}, {3, 3, 2}, {2, 2, 3}, {2, 2, 2}, {1, 1, 2}, {1, 1, 1}, {0, 0, 1}};
-  const int64_t budget = 227 * 1024;
-  {
-    const char *d = getenv("WSIS_CONV_NREC");
-    p.nrec = d ? std::max(2, std::min(kMaxRec, atoi(d))) : 2;
-  }
   int64_t smem = 0;
-  bool fit = false;
-  for (auto &c : pref) {
-    const int na = 1 << c[0], nrc = c[2];
-    const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nrc + 2 * p.nrec + 4) * 8 + 64;
-    smem = misc + na * (a_stage + w_stage) + nrc * rc_buf + p.nrec * rec_buf;
-    if (smem <= budget) {
-      p.lna = c[0];
-      p.lnw = c[1];
-      p.nrc = nrc;
-      p.nb = std::min(kBuildWarps / 2, na);  // stage owners; two warps each
-      p.nmma = std::min(p.nmma, na);  // every A/W stage belongs to exactly one issuer
-      fit = true;
-      break;
-    }
-  }
-  WSIS_CHECK(fit, "conv_umma: shared memory budget exceeded for Cin=%d Cout=%d K=%d", Cin, Cout, K);
+  if (plan_launch(p, K, Cin, Cout, NS, max_record_bytes, &smem)) return 1;
   auto kern = NS == 2 ? conv_umma_kernel<2> : conv_umma_kernel<1>;
   static int64_t smem_set[2] = {0, 0};
   if (smem > smem_set[NS - 1]) {

@@ -151,6 +151,10 @@ int wsis_conv_umma_supported(int Cin, int Cout);
 int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision);
 int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
                            wsis_stream_t stream);
+/* Launch plan of a layer shape (pure host arithmetic, no device needed): plan = int32[8] {dynamic shared-memory bytes,
+ * pipeline stages, row-cache buffers, record buffers, builder stage owners, TMEM accumulators, MMA issuers, TMEM columns}.
+ * Fails when no pipeline fits the 227 KB of shared memory. */
+int wsis_conv_umma_plan(int K, int Cin, int Cout, int precision, int max_record_bytes, int32_t *plan);
 int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, const int32_t *meta,
                    const int32_t *order, int64_t num_tiles, int K, int max_record_bytes, const void *packed, int Cin,
                    int Cout, int precision,

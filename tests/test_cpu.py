@@ -505,3 +505,29 @@ def test_clustering_fragments_and_edge_cases():
     # without any primary instance the reference would index an empty list; here the result is simply empty
     conf, label, masks = cluster.clustering_in_graph(xyz, sp, nbrs, np.array([1, 1, 1, 1, 1]), off, occ, size)
     assert len(conf) == 0 and masks.shape == (0, len(xyz))
+
+
+def test_conv_umma_launch_plan_exists_for_every_layer_shape():
+    """Host-only: every (Cin, Cout, K, precision) the tensor-core conv accepts has a pipeline that fits the 227 KB of
+    shared memory and the 512 TMEM columns, and the invariants the kernel's barrier protocol relies on hold (stages are
+    a power of two, every stage has one issuer and one builder pair: nb | stages, nmma | stages)."""
+    from wsis_b200._lib import lib
+    L = lib()
+    shapes = [(6, 32), (32, 32), (64, 32), (32, 64), (64, 64), (128, 64), (96, 96), (192, 96), (128, 128), (256, 128),
+              (160, 160), (320, 160), (160, 128), (1, 16), (1024, 256), (33, 240)]
+    for cin, cout in shapes:
+        for K in (1, 8, 27, 32):
+            for prec in (1, 3):
+                plan = (ctypes.c_int32 * 8)()
+                L.call("wsis_conv_umma_plan", K, cin, cout, prec, 0, plan)
+                smem, na, nrc, nrec, nb, nacc, nmma, cols = list(plan)
+                assert 0 < smem <= 227 * 1024, (cin, cout, K, prec, smem)
+                assert na in (1, 2, 4, 8) and nrc >= 1 and nrec >= 2
+                assert na % nb == 0 and na % nmma == 0 and nacc % nmma == 0
+                assert 2 * nacc * cout <= cols <= 512 and cols & (cols - 1) == 0
+    # the model's widest layers keep at least 4 stages in the fp32 contract
+    plan = (ctypes.c_int32 * 8)()
+    L.call("wsis_conv_umma_plan", 27, 32, 32, 3, 0, plan)
+    assert plan[1] >= 4
+    with pytest.raises(RuntimeError):
+        L.call("wsis_conv_umma_plan", 27, 32, 24, 3, 0, plan)      # Cout not a multiple of 16
