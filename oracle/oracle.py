@@ -187,6 +187,40 @@ def edge_attention(q, k, v, ecc, centers, eu, ev, w1, b1, w2, b2):
     return aff, sp
 
 
+def ecc_gru_step(h, filters, src, tgt, w_ig, b_ig, w_ih, w_hh, b_ih, b_hh, layernorm=True, eps=1e-5):
+    """One step of the edge-conditioned GRU in float64 numpy.
+    NNConv with aggr='mean', no root weight, no bias (modules/model/spg_modules.py:97-121: messages x[src]^T W_e,
+    averaged at the edge's target; superpoints without an in-edge get 0), then GRUCellEx (:226-253): input gate
+    sigmoid(ig(h)) * m, gate pre-activations inp.W_ih^T and h.W_hh^T each normalised by InstanceNorm1d(1) = un-affine
+    layer norm with biased variance, reset / update / new gates, h' = n + z (h - n).
+    h [S,F]; filters [E,F*F] ([in][out]); src, tgt int[E]; w_ig [F,F], b_ig [F]; w_ih, w_hh [3F,F]; b_ih, b_hh [3F]."""
+    h = np.asarray(h, np.float64)
+    S, F = h.shape
+    W = np.asarray(filters, np.float64).reshape(-1, F, F)
+    msg = np.einsum("ei,eio->eo", h[src], W)
+    m = np.zeros((S, F))
+    np.add.at(m, tgt, msg)
+    m /= np.maximum(np.bincount(tgt, minlength=S), 1)[:, None]
+
+    def sig(x):
+        return 1.0 / (1.0 + np.exp(-x))
+
+    def ln(x):
+        x = x - x.mean(1, keepdims=True)
+        return x / np.sqrt((x * x).mean(1, keepdims=True) + eps)
+
+    inp = sig(h @ np.asarray(w_ig, np.float64).T + np.asarray(b_ig, np.float64)) * m
+    gi = inp @ np.asarray(w_ih, np.float64).T
+    gh = h @ np.asarray(w_hh, np.float64).T
+    if layernorm:
+        gi, gh = ln(gi), ln(gh)
+    b_ih, b_hh = np.asarray(b_ih, np.float64), np.asarray(b_hh, np.float64)
+    r = sig(gi[:, :F] + b_ih[:F] + gh[:, :F] + b_hh[:F])
+    z = sig(gi[:, F:2 * F] + b_ih[F:2 * F] + gh[:, F:2 * F] + b_hh[F:2 * F])
+    n = np.tanh(gi[:, 2 * F:] + b_ih[2 * F:] + r * (gh[:, 2 * F:] + b_hh[2 * F:]))
+    return n + z * (h - n)
+
+
 def weak_label_propagation(sp_semantic_label, adjacency, sp_semantic_value, sp_pred_semantic, affinity_matrix,
                            iterations_num, class_num=20):
     """Random-walk label propagation, restating modules/datasets/scannetv2_dataset.py:664-735 in numpy

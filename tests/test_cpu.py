@@ -531,3 +531,26 @@ def test_conv_umma_launch_plan_exists_for_every_layer_shape():
     assert plan[1] >= 4
     with pytest.raises(RuntimeError):
         L.call("wsis_conv_umma_plan", 27, 32, 24, 3, 0, plan)      # Cout not a multiple of 16
+
+
+def test_oracle_ecc_gru_step_matches_module(orc):
+    """The numpy restatement of one ECC-GRU step (oracle.ecc_gru_step) against the torch formulation of
+    spg_modules.py:97-121 / 226-253 in wsis_b200.model (which the golden network outputs pin to the reference)."""
+    from wsis_b200 import model as M
+    torch.manual_seed(7)
+    rng = np.random.default_rng(7)
+    S, E = 60, 300
+    for layernorm in (True, False):
+        cell = M.GRUCellEx(32, 32, bias=True, layernorm=layernorm, ingate=True).double()
+        nn_ = M.NNConv(32, 32)
+        src, tgt = rng.integers(0, S, E), rng.integers(0, S - 5, E)
+        h = torch.from_numpy(rng.standard_normal((S, 32)))
+        w = torch.from_numpy(rng.standard_normal((E, 1024)) * 0.2)
+        ei = torch.from_numpy(np.stack([src, tgt]))
+        with torch.no_grad():
+            ref = cell(nn_(h, ei, w), h).numpy()
+        out = orc.ecc_gru_step(h.numpy(), w.numpy(), src, tgt, cell._modules["ig"].weight.detach().numpy(),
+                               cell._modules["ig"].bias.detach().numpy(), cell.weight_ih.detach().numpy(),
+                               cell.weight_hh.detach().numpy(), cell.bias_ih.detach().numpy(),
+                               cell.bias_hh.detach().numpy(), layernorm=layernorm)
+        assert np.abs(out - ref).max() < 1e-10

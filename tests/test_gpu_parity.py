@@ -708,7 +708,7 @@ def test_s3dis_shaped_room_full_size_properties(W):
 
 
 @pytest.mark.parametrize("S,E,layernorm", [(700, 6000, True), (50, 40, True), (300, 2500, False), (33, 1, True)])
-def test_ecc_gru_fused_matches_module(W, S, E, layernorm):
+def test_ecc_gru_fused_matches_module(W, orc, S, E, layernorm):
     """csrc/ecc.cu (one kernel per GRU step) against the module-by-module torch formulation of
     spg_modules.py:152-185 / 226-253 (NNConv mean aggregation + GRUCellEx), which the golden network test pins to the
     reference.  Includes superpoints without in-edges, unsorted targets and duplicate edges."""
@@ -730,3 +730,14 @@ def test_ecc_gru_fused_matches_module(W, S, E, layernorm):
     assert out.shape == ref.shape == (S, 32 * 8)
     assert torch.equal(out[:, :32], hx)
     assert rel(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+    # and against the float64 oracle, step by step from the kernel's own previous state
+    ig = cell._modules["ig"]
+    with torch.no_grad():
+        w = fnet.cuda()(feats).cpu().numpy()
+    o = out.cpu().numpy()
+    for r in range(7):
+        exp = orc.ecc_gru_step(o[:, 32 * r:32 * r + 32], w, src, tgt, ig.weight.detach().cpu().numpy(),
+                               ig.bias.detach().cpu().numpy(), cell.weight_ih.detach().cpu().numpy(),
+                               cell.weight_hh.detach().cpu().numpy(), cell.bias_ih.detach().cpu().numpy(),
+                               cell.bias_hh.detach().cpu().numpy(), layernorm=layernorm)
+        assert rel(o[:, 32 * r + 32:32 * r + 64], exp) < 2e-5
