@@ -554,3 +554,38 @@ def test_oracle_ecc_gru_step_matches_module(orc):
                                cell.weight_hh.detach().numpy(), cell.bias_ih.detach().numpy(),
                                cell.bias_hh.detach().numpy(), layernorm=layernorm)
         assert np.abs(out - ref).max() < 1e-10
+
+
+def test_conv_umma_barrier_protocol_model():
+    """tools/protocol_model.py transcribes the control flow of every role of conv_umma_kernel (ring indices, parities,
+    arrival counts) and checks under random schedules that no parity wait passes before its logical generation has
+    completed, that every consumer finds the buffer contents it expects, and that nothing deadlocks -- for every
+    launch plan the host planner can produce.  The configuration that once hung on the GPU (more builder warps than
+    operand stages) and a stage shared by two issuers must be caught."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import protocol_model as pm
+    from wsis_b200._lib import lib
+    L = lib()
+    plans = set()
+    for cin, cout in [(6, 32), (32, 32), (64, 64), (96, 96), (128, 128), (160, 160), (320, 160), (1024, 256), (32, 16)]:
+        for K in (8, 27, 32):
+            for prec in (1, 3):
+                plan = (ctypes.c_int32 * 8)()
+                L.call("wsis_conv_umma_plan", K, cin, cout, prec, 0, plan)
+                _, na, nrc, nrec, nb, _, nmma, _ = list(plan)
+                plans.add((na, nrc, nrec, nb, nmma))
+    assert len(plans) >= 3
+    rng = random.Random(5)
+    for na, nrc, nrec, nb, nmma in sorted(plans):
+        for seed in range(12):
+            tiles = pm.random_tiles(rng, rng.randint(1, 7))
+            assert pm.Cta(tiles, na, nrc, nrec, nb, nmma).run(seed)
+        assert pm.Cta([(1, 1)], na, nrc, nrec, nb, nmma).run(0)              # a single one-unit tile
+        assert pm.Cta([(27, 5)] * 3, na, nrc, nrec, nb, nmma).run(1)         # the widest layer
+    with pytest.raises(pm.ProtocolError):                                    # 6 single-warp builders on 4 stages
+        for seed in range(50):
+            pm.Cta(pm.random_tiles(rng, 6), 4, 3, 2, 6, 2, builder_halves=1).run(seed)
+    with pytest.raises(pm.ProtocolError):                                    # two issuers alternate on one stage
+        for seed in range(50):
+            pm.Cta(pm.random_tiles(rng, 6), 1, 2, 2, 1, 2).run(seed)
