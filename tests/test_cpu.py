@@ -589,3 +589,31 @@ def test_conv_umma_barrier_protocol_model():
     with pytest.raises(pm.ProtocolError):                                    # two issuers alternate on one stage
         for seed in range(50):
             pm.Cta(pm.random_tiles(rng, 6), 1, 2, 2, 1, 2).run(seed)
+
+
+def test_label_propagation_matches_reference_golden():
+    """tests/golden/make_golden_labels.py ran the reference's extend_label_to_neighbor / propagate_label_to_neighbor /
+    propagate_label_to_whole_scene (scannetv2_dataset.py:779-958) on this scene; the array-based versions must give the
+    same labels, the same offsets and the same per-edge is1ins."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_labels as mg
+    from wsis_b200 import labels as LB
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "labels_scene0.npz"))
+    case = mg.make_case(int(gold["seed"]), int(gold["n_points"]))
+    geo = LB.SuperpointGeometry(case["xyz"], case["superpoint"])
+    start = LB.SuperpointLabels(case["sem"], case["ins"], case["off"])
+
+    def check(res, key, edges=True):
+        assert np.array_equal(res.semantic, gold[key + "_sem"]) and np.array_equal(res.instance, gold[key + "_ins"])
+        assert np.array_equal(res.offset, gold[key + "_off"])
+        if edges:
+            assert np.array_equal(LB.edge_same_instance(case["edges"], res), gold[key + "_is1ins"])
+
+    ext = LB.extend_label_to_neighbor(start, geo, case["nbrs"], case["conf"], case["pred"])
+    check(ext, "ext")
+    assert (ext.semantic != -100).sum() > (start.semantic != -100).sum()
+    prop = LB.propagate_label_to_neighbor(ext, geo, case["nbrs"], case["conf"], case["pred"])
+    check(prop, "prop")
+    whole = LB.propagate_label_to_whole_scene(start, geo, case["pred"], case["pred_off"])
+    check(whole, "whole", edges=False)
+    assert np.array_equal(start.semantic, case["sem"])            # the inputs are not modified
