@@ -111,7 +111,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def wait_ready(self, timeout=5.0):
+    def wait_ready(self, timeout=20.0):
         """nvidia-smi start-up (NVML initialisation) takes the driver lock and stalled concurrent launches for up to
         0.5 s when it overlapped a timed step: the sampler is started before the warm-up and must be streaming before
         any timing begins; it is terminated only after every timed region."""
