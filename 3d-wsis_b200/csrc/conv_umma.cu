@@ -200,8 +200,9 @@ struct Params {
   unsigned long long *tl;  // optional timeline buffer (wsis_conv_debug_timeline): [0] = event count, then (time, code)
   int tl_cap;
   int dbg;  // WSIS_CONV_DEBUG bits (timing experiments only; results are wrong): 1 no MMA, 2 no build, 4 no gather, 8 no weight copy
-  int lna, lnw, nrc, nrec, nb, nacc, nmma, tmem_cols;
-  int rec_main;  // shared-memory bytes reserved for one entry record (>= the largest meta[t].x of this tile map)  // A ring = 1 << lna stages, W ring = 1 << lnw, nb active builders
+  int lna, nrc, nrec, nb, nacc, nmma, tmem_cols;  // 1 << lna pipeline stages, nrc row-cache buffers, nrec record
+                                                  // buffers, nb stage-owning builder pairs, TMEM accumulators, issuers
+  int rec_main;  // shared-memory bytes reserved for one entry record (>= the largest meta[t].x of this tile map)
   int64_t num_tiles;
 };
 
@@ -748,29 +749,25 @@ static int plan_launch(wsis::umma::Params &p, int K, int Cin, int Cout, int NS, 
   int cols = 32;
   while (cols < 2 * nacc * Cout) cols <<= 1;
   p.tmem_cols = cols;
-  // shared memory: A ring (2^lna stages), weight ring (2^lnw), row cache (nrc buffers), records; shrink the rings
-  // in this order of preference until the layer fits
+  // shared memory: 2^lna pipeline stages (operand + weight blocks), nrc row-cache buffers, nrec record buffers;
+  // shrink in this order of preference until the layer fits
   const int64_t a_stage = (int64_t)NS * kABlockBytes, w_stage = (int64_t)NS * Cout * 64;
   // the record buffers are sized for the largest record of THIS tile map when the caller knows it (0 = worst case)
   WSIS_CHECK(max_record_bytes >= 0 && max_record_bytes % 16 == 0 && max_record_bytes <= rec_stride_bytes(K),
              "conv_umma: max_record_bytes %d must be a multiple of 16 in [0, %d]", max_record_bytes, rec_stride_bytes(K));
   p.rec_main = max_record_bytes ? max_record_bytes : rec_stride_bytes(K);
   const int64_t rc_buf = (int64_t)kRcap * NS * 64, rec_buf = p.rec_main + kRcap * 4;
-  static const int pref[][3] = {{3, 3, 3}, {3, 3, 2}, {2, 2, 3}, {2, 2, 2}, {1, 1, 2}, {1, 1, 1}, {0, 0, 1}};
+  static const int pref[][2] = {{3, 3}, {3, 2}, {2, 3}, {2, 2}, {1, 2}, {1, 1}, {0, 1}};  // {lna, nrc}
   const int64_t budget = 227 * 1024;
-  {
-    const char *d = getenv("WSIS_CONV_NREC");
-    p.nrec = d ? std::max(2, std::min(kMaxRec, atoi(d))) : 2;
-  }
+  p.nrec = 2;  // more record buffers did not pay (profiles/README.md); the kernel supports up to kMaxRec
   int64_t smem = 0;
   bool fit = false;
   for (auto &c : pref) {
-    const int na = 1 << c[0], nrc = c[2];
+    const int na = 1 << c[0], nrc = c[1];
     const int64_t misc = 1024 /*align*/ + 2 * p.KB * kKB * 4 + na * 16 + (2 * na + 2 * nrc + 2 * p.nrec + 4) * 8 + 64;
     smem = misc + na * (a_stage + w_stage) + nrc * rc_buf + p.nrec * rec_buf;
     if (smem <= budget) {
       p.lna = c[0];
-      p.lnw = c[1];
       p.nrc = nrc;
       p.nb = std::min(kBuildWarps / 2, na);  // stage owners; two warps each
       p.nmma = std::min(p.nmma, na);  // every A/W stage belongs to exactly one issuer
