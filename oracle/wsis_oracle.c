@@ -7,7 +7,7 @@
  * CUDA path against.  Nothing in the product package (3d-wsis_b200/) may import, link or execute
  * this file: the product path fails loudly when its CUDA library is missing.
  *
- * Pinning (see tests/test_oracle_cpu.py):
+ * Pinning (see tests/test_cpu.py):
  *   - rulebooks and sparse convs are checked against the UNMODIFIED reference spconv CPU path
  *     compiled from the reference's own sources (oracle/_ref/libspconv_ref.so, oracle/Makefile) and
  *     against the dense nn.Conv3d equivalence that the reference's own test uses
