@@ -216,6 +216,32 @@ int64_t wsis_voxelize_idx_host(const int64_t *coords, int64_t N, int64_t *voxel_
   return M;
 }
 
+int wsis_voxelize_idx_host_fill(const int64_t *coords, int64_t N, const int32_t *p2v, int64_t M, int64_t *voxel_locs,
+                                int32_t *v2p, int32_t v2p_stride) {
+  // second phase of the host routine when the caller kept the p2v of the counting call: one linear pass, no hashing
+  if (N < 0 || M < 0 || v2p_stride < 1) {
+    set_error("voxelize_idx_host_fill: bad sizes");
+    return 1;
+  }
+  memset(v2p, 0, sizeof(int32_t) * (size_t)M * v2p_stride);
+  for (int64_t i = 0; i < N; ++i) {
+    const int32_t m = p2v[i];
+    if (m < 0 || m >= M) {
+      set_error("voxelize_idx_host_fill: p2v[%lld] = %d outside [0, %lld)", (long long)i, m, (long long)M);
+      return 1;
+    }
+    int32_t *row = v2p + (int64_t)m * v2p_stride;
+    const int32_t k = row[0]++;
+    if (1 + k >= v2p_stride) {
+      set_error("voxelize_idx_host_fill: v2p_stride %d too small", v2p_stride);
+      return 1;
+    }
+    if (k == 0) memcpy(voxel_locs + (int64_t)m * 4, coords + i * 4, sizeof(int64_t) * 4);
+    row[1 + k] = (int32_t)i;
+  }
+  return 0;
+}
+
 int64_t wsis_voxelize_ws_bytes(int64_t N) { return carve(nullptr, N).bytes; }
 
 int wsis_voxelize_idx_count(const int64_t *coords, int64_t N, int32_t *p2v, int32_t *counts_dev, void *ws,

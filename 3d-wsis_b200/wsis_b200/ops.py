@@ -390,16 +390,14 @@ def voxelization_idx(coords, batch_size=None, mode=4):
     N = coords.shape[0]
     if not coords.is_cuda:
         ma = ctypes.c_int32(0)
-        M = lib().value("wsis_voxelize_idx_host", _ptr(coords), N, None, None, None, 0, ctypes.byref(ma))
+        p2v = torch.empty((N,), dtype=torch.int32)
+        # phase 1 hashes the points once (voxel count, max points per voxel, p2v); phase 2 is a linear fill
+        M = lib().value("wsis_voxelize_idx_host", _ptr(coords), N, None, _ptr(p2v), None, 0, ctypes.byref(ma))
         if M < 0:
             raise RuntimeError("voxelization_idx: " + lib().last_error())
         locs = torch.empty((M, 4), dtype=torch.int64)
-        p2v = torch.empty((N,), dtype=torch.int32)
         v2p = torch.empty((M, 1 + ma.value), dtype=torch.int32)
-        M2 = lib().value("wsis_voxelize_idx_host", _ptr(coords), N, _ptr(locs), _ptr(p2v), _ptr(v2p), 1 + ma.value,
-                         ctypes.byref(ma))
-        if M2 != M:
-            raise RuntimeError("voxelization_idx: " + lib().last_error())
+        lib().call("wsis_voxelize_idx_host_fill", _ptr(coords), N, _ptr(p2v), M, _ptr(locs), _ptr(v2p), 1 + ma.value)
         return locs, p2v, v2p
     dev = coords.device
     p2v = torch.empty((N,), dtype=torch.int32, device=dev)

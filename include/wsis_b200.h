@@ -183,6 +183,10 @@ int wsis_affine_relu(const float *x, int64_t n, int C, const float *scale, const
  * then with buffers voxel_locs int64[M,4], p2v int32[N], v2p int32[M,1+max_active] (zero-filled by the call). */
 int64_t wsis_voxelize_idx_host(const int64_t *coords_host, int64_t N, int64_t *voxel_locs_host, int32_t *p2v_host,
                                int32_t *v2p_host, int32_t v2p_stride, int32_t *max_active_host);
+/* Second phase without re-hashing: p2v = the point -> voxel map the counting call (voxel_locs = NULL, p2v != NULL) wrote,
+ * M = its return value, v2p_stride >= 1 + max_active.  Fills voxel_locs int64[M,4] and v2p int32[M, v2p_stride]. */
+int wsis_voxelize_idx_host_fill(const int64_t *coords, int64_t N, const int32_t *p2v, int64_t M, int64_t *voxel_locs,
+                                int32_t *v2p, int32_t v2p_stride);
 
 /* Device voxelization_idx (same numbering: first-occurrence order; v2p lists in ascending point order).
  * Phase 1: p2v int32[N] out; counts_dev int32[3]: [0] = M, [1] = max_active, [2] = 1 if a coordinate was
