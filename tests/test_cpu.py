@@ -617,3 +617,33 @@ def test_label_propagation_matches_reference_golden():
     whole = LB.propagate_label_to_whole_scene(start, geo, case["pred"], case["pred_off"])
     check(whole, "whole", edges=False)
     assert np.array_equal(start.semantic, case["sem"])            # the inputs are not modified
+
+
+def test_label_propagation_edge_cases():
+    """No labeled superpoint: nothing changes.  A labeled superpoint hands its label only to unlabeled neighbours whose
+    predicted class agrees (and, for the extension, whose confidence exceeds 0.8); whole-scene propagation ignores
+    superpoints whose predicted class has no prior or whose nearest prior is farther than 0.9 m."""
+    from wsis_b200 import cluster, labels as LB
+    xyz = np.array([[0, 0, 0], [0.1, 0, 0], [1, 0, 0], [1.1, 0, 0], [5, 0, 0], [5.1, 0, 0], [0.5, 0, 0]], np.float32)
+    sp = np.array([0, 0, 1, 1, 2, 2, 3])
+    nbrs = cluster.neighbors_from_edges(np.array([[0, 1], [1, 2], [0, 3]]), 4)
+    assert nbrs == [[1, 3], [0, 2], [1], [0]]
+    geo = LB.SuperpointGeometry(xyz, sp)
+    assert np.allclose(geo.centre[:, 0], [0.05, 1.05, 5.05, 0.5]) and list(geo.count) == [2, 2, 2, 1]
+    none = LB.SuperpointLabels([-100] * 4, [-100] * 4, np.zeros((4, 3)))
+    pred, conf = np.array([3, 3, 3, 7]), np.array([0.9, 0.95, 0.5, 0.99])
+    for fn in (LB.extend_label_to_neighbor, LB.propagate_label_to_neighbor):
+        out = fn(none, geo, nbrs, conf, pred)
+        assert np.array_equal(out.semantic, none.semantic) and not out.offset.any()
+    start = LB.SuperpointLabels([3, -100, -100, -100], [11, -100, -100, -100], np.array([[0.2, 0, 0]] + [[0, 0, 0]] * 3))
+    ext = LB.extend_label_to_neighbor(start, geo, nbrs, conf, pred)
+    assert list(ext.semantic) == [3, 3, -100, -100] and list(ext.instance) == [11, 11, -100, -100]   # 3: other class
+    assert np.allclose(ext.offset[1], [0.05 + 0.2 - 1.05, 0, 0])      # points at superpoint 0's instance centre
+    assert list(LB.edge_same_instance(np.array([[0, 1], [1, 2], [0, 3]]), ext)) == [-1, 0, 0]
+    prop = LB.propagate_label_to_neighbor(ext, geo, nbrs, conf, pred)  # no confidence test: 2 joins through 1
+    assert list(prop.semantic) == [3, 3, 3, -100]
+    whole = LB.propagate_label_to_whole_scene(start, geo, pred, np.zeros((4, 3), np.float32))
+    # prior instance centre = 0.05 + 0.2 = 0.25: superpoint 1 (1.05, distance 0.8 < 0.9) joins, 2 (5.05) is too far,
+    # 3 predicts a class without a prior
+    assert list(whole.semantic) == [3, 3, -100, -100] and list(whole.instance) == [11, 11, -100, -100]
+    assert np.allclose(whole.offset[1], 0)                            # the centroid of its own points
