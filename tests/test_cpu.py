@@ -647,3 +647,22 @@ def test_label_propagation_edge_cases():
     # 3 predicts a class without a prior
     assert list(whole.semantic) == [3, 3, -100, -100] and list(whole.instance) == [11, 11, -100, -100]
     assert np.allclose(whole.offset[1], 0)                            # the centroid of its own points
+
+
+def test_bench_clock_sampler_summary_window_and_reasons():
+    """bench.py's clock line: only samples taken inside the timed window count, throttle reasons are collected, and a
+    missing nvidia-smi is reported instead of crashing."""
+    sys.path.insert(0, ROOT)
+    import bench
+    cs = bench.ClockSampler(0)
+    cs.proc = object()                                           # "running"
+    mk = lambda sm, hw, pc: "0, %d, 1965, 400.0, %s, Not Active, Not Active, %s" % (sm, hw, pc)
+    cs.lines = [(10.0, mk(300, "Not Active", "Not Active")),     # before the window (idle clocks)
+                (20.0, mk(1965, "Not Active", "Not Active")), (20.1, mk(1950, "Not Active", "Active")),
+                (20.2, mk(1965, "Not Active", "Not Active")), (30.0, mk(500, "Active", "Not Active"))]
+    out = cs.summary(19.9, 20.25)
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965 and out["sm_max_mhz"] == 1965
+    assert out["reasons"] == ["sw_power_cap"]                     # the hw_slowdown sample lies outside the window
+    assert cs.summary(100.0, 101.0)["samples"] == 3               # nothing inside: falls back to the last samples
+    cs.proc = None
+    assert cs.summary(0, 1)["reasons"] == ["nvidia-smi unavailable"]
