@@ -91,9 +91,9 @@ __device__ __forceinline__ int64_t hash_find(const unsigned long long *__restric
 }
 
 // tile record geometry (tilemap.cu builds the records, conv_umma.cu consumes them)
-//   valid[K][4] u32 | start[K+1] u16, nU u16 | eloc[P] u16 | eslot[P] u8      (P <= 128 K)
-__host__ __device__ __forceinline__ int rec_hdr_bytes(int K) { return 16 * K + ((2 * (K + 2) + 15) & ~15); }
-__host__ __device__ __forceinline__ int rec_stride_bytes(int K) { return (rec_hdr_bytes(K) + 3 * 128 * K + 15) & ~15; }
+//   valid[K][4] u32 | {nU u32, amask u32, P u32, nact u32, klist u8[32]} | loc[K][128] u16
+__host__ __device__ __forceinline__ int rec_hdr_bytes(int K) { return 16 * K + 48; }
+__host__ __device__ __forceinline__ int rec_stride_bytes(int K) { return rec_hdr_bytes(K) + 256 * K; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -41,17 +41,18 @@ __global__ void iota_kernel(int32_t *order, int64_t N, int64_t n_pad) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile records: what one conv CTA needs to know about one tile of 128 destination rows, compacted.
-//   entry record (records + t * rec_stride_bytes(K), meta[t].x bytes of it are meaningful)
-//     [0, 16K)              valid[K][4]  u32   bit r of valid[k] = tile slot r has a source row through offset k
-//     [16K, hdr)            start[K+1]   u16   entries of offset k are [start[k], start[k+1]);  then nU u16
-//     [hdr, hdr + 2P)       eloc[P]      u16   index of the entry's source row in the tile's UNIQUE-row list
-//     [hdr + 2P, hdr + 3P)  eslot[P]     u8    tile slot (accumulator lane) of the entry, ascending inside an offset
-//   unique rows (uidx + t * 128K)  i32[nU]     the distinct source rows the tile reads; a surface patch of 128
-//                                              voxels reads ~160-230 distinct rows through ~480-1400 entries, so the
-//                                              conv kernel fetches (and converts) every source row ONCE per tile
-//   meta[t] = {entry-record bytes, nU, active-offset mask (1 if the tile has no entry at all), P}
-// Records live at a fixed stride (worst case P = 128K) so they are built in one pass without a size scan.
+// Tile records: what one conv CTA needs to know about one tile of 128 destination rows.
+//   record (records + t * rec_stride_bytes(K), all of it meaningful)
+//     [0, 16K)                 valid[K][4]  u32   bit r of valid[k] = tile slot r has a source row through offset k
+//     [16K, 16K + 48)          nU u32 | amask u32 | P u32 | nact u32 | klist u8[32]: the nact active offsets, ascending
+//     [16K + 48, 16K+48+256K)  loc[K][128]  u16   index of slot r's source row through offset k in the tile's list of
+//                                                 DISTINCT source rows (0xFFFF where valid[k] has no bit)
+//   unique rows (uidx + t * 128K)  i32[nU]        the distinct source rows the tile reads; a surface patch of 128
+//                                                 voxels reads ~160-230 distinct rows through ~480-1400 entries, so the
+//                                                 conv kernel fetches (and converts) every source row ONCE per tile
+//   meta[t] = {record bytes, nU, active-offset mask (1 if the tile has no entry at all), P}
+// The dense [K][128] form is what the conv kernel's operand builders want: builder thread r owns tile slot r (= the
+// TMEM lane of that row) and reads loc[k][r] with a conflict-free 16-bit load.
 // ------------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t tile_hash(int32_t v, uint32_t mask) {
@@ -63,26 +64,34 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
                                                             int32_t *__restrict__ uidx, int4 *__restrict__ meta,
                                                             int32_t *__restrict__ stats) {
   extern __shared__ int32_t s_map[];  // [K][128] transposed slice
-  int32_t *s_cnt = s_map + K * kTile;                                   // [4K + 1] entry prefix, [4] table prefix
-  int32_t *s_tab = s_cnt + 4 * K + 8;                                   // [HT] open-addressing set of source rows
-  uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_tab + HT);           // [K][128] table slot of each entry
+  int32_t *s_cnt = s_map + K * kTile;                                   // [K] entries per offset
+  int32_t *s_tab = s_cnt + K + 8;                                       // [HT] open-addressing set of source rows
+  int32_t *s_first = s_tab + HT;                                        // [HT] first entry (k * 128 + slot) of the row
+  uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_first + HT);        // [4 K] bitmap of first entries
+  int32_t *s_pre = reinterpret_cast<int32_t *>(s_bits + 4 * K);         // [4 K + 1] exclusive prefix of its popcounts
+  uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_pre + 4 * K + 4);    // [K][128] table slot of each entry
   const int64_t t = blockIdx.x;
   const int r = threadIdx.x, lane = r & 31, w = r >> 5;
   const int32_t dst = __ldg(order + t * kTile + r);
   for (int k = 0; k < K; ++k)
     s_map[k * kTile + r] = dst >= 0 ? __ldg(map + (int64_t)dst * K + (flip ? K - 1 - k : k)) : -1;
-  for (int i = r; i < HT; i += kTile) s_tab[i] = -1;
+  for (int i = r; i < HT; i += kTile) {
+    s_tab[i] = -1;
+    s_first[i] = 0x7fffffff;
+  }
+  for (int i = r; i < 4 * K; i += kTile) s_bits[i] = 0u;
+  if (r < K) s_cnt[r] = 0;
   __syncthreads();
   uint8_t *rec = recs + t * (int64_t)rec_stride_bytes(K);
   uint32_t *valid = reinterpret_cast<uint32_t *>(rec);
-  uint16_t *start = reinterpret_cast<uint16_t *>(rec + 16 * K);
-  // per-offset population (one warp ballot per 32 slots) and insertion of the source rows into the set
+  // per-offset population (one warp ballot per 32 slots), insertion of the source rows into the set, and the FIRST
+  // entry (in offset-major, slot-minor order) that reads each row
   for (int k = 0; k < K; ++k) {
     const int32_t v = s_map[k * kTile + r];
     const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
     if (lane == 0) {
       valid[k * 4 + w] = bal;
-      s_cnt[k * 4 + w] = __popc(bal);
+      if (bal) atomicAdd(s_cnt + k, __popc(bal));
     }
     if (v >= 0) {
       uint32_t h = tile_hash(v, HT - 1);
@@ -92,60 +101,65 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
         h = (h + 1) & (HT - 1);
       }
       s_pos[k * kTile + r] = (uint16_t)h;
+      atomicMin(s_first + h, k * kTile + r);
     }
   }
   __syncthreads();
-  if (r == 0) {  // exclusive prefix over (offset, warp) -- K*4 <= 128 values
+  // Distinct rows are numbered in first-entry order: consecutive slots that read new rows through an offset get
+  // consecutive indices, so the 32 lanes of a conv builder warp (consecutive slots, one offset) read row-cache rows
+  // whose indices mostly differ in their low bits -> different shared-memory bank groups (conv_umma.cu, rc_swz).
+  for (int k = 0; k < K; ++k) {
+    const bool first = s_map[k * kTile + r] >= 0 && s_first[s_pos[k * kTile + r]] == k * kTile + r;
+    const uint32_t bal = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) s_bits[k * 4 + w] = bal;
+  }
+  __syncthreads();
+  if (w == 0) {  // exclusive prefix over the 4 K <= 128 bitmap words
     int run = 0;
-    for (int i = 0; i < K * 4; ++i) {
-      int c = s_cnt[i];
-      s_cnt[i] = run;
-      run += c;
+    for (int i0 = 0; i0 < 4 * K; i0 += 32) {
+      const int i = i0 + lane;
+      const int c = i < 4 * K ? __popc(s_bits[i]) : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (i < 4 * K) s_pre[i] = run + inc - c;
+      run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    s_cnt[K * 4] = run;
+    if (lane == 0) s_pre[4 * K] = run;
   }
-  // compaction of the set: warp w owns table quarter w; pass 1 counts, pass 2 ranks (table slot -> unique index)
-  const int q0 = w * (HT / 4), q1 = q0 + HT / 4;
-  int cnt = 0;
-  for (int i = q0 + lane; i < q1; i += 32) cnt += __popc(__ballot_sync(0xffffffffu, s_tab[i] >= 0)) * (lane == 0);
-  if (lane == 0) s_cnt[4 * K + 1 + w] = cnt;
   __syncthreads();
-  int base = 0;
-  for (int i = 0; i < w; ++i) base += s_cnt[4 * K + 1 + i];
-  const int nU = s_cnt[4 * K + 1] + s_cnt[4 * K + 2] + s_cnt[4 * K + 3] + s_cnt[4 * K + 4];
+  const int nU = s_pre[4 * K];
   int32_t *u = uidx + t * (int64_t)(kTile * K);
-  for (int i = q0 + lane; i < q1; i += 32) {
-    const int32_t v = s_tab[i];
-    const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
-    if (v >= 0) {
-      const int rank = base + __popc(bal & ((1u << lane) - 1u));
-      u[rank] = v;
-      s_tab[i] = rank;
-    }
-    base += __popc(bal);
-  }
-  __syncthreads();
-  const int P = s_cnt[K * 4];
-  if (r <= K) start[r] = (uint16_t)(r < K ? s_cnt[r * 4] : P);
-  if (r == 0) start[K + 1] = (uint16_t)nU;
-  uint16_t *eloc = reinterpret_cast<uint16_t *>(rec + rec_hdr_bytes(K));
-  uint8_t *eslot = rec + rec_hdr_bytes(K) + 2 * P;
+  uint16_t *loc = reinterpret_cast<uint16_t *>(rec + rec_hdr_bytes(K));
   for (int k = 0; k < K; ++k) {
     const int32_t v = s_map[k * kTile + r];
-    const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
+    uint16_t l = 0xFFFFu;
     if (v >= 0) {
-      const int pos = s_cnt[k * 4 + w] + __popc(bal & ((1u << lane) - 1u));
-      eloc[pos] = (uint16_t)s_tab[s_pos[k * kTile + r]];
-      eslot[pos] = (uint8_t)r;
+      const int key = s_first[s_pos[k * kTile + r]];  // first entry of this row
+      const int rank = s_pre[key >> 5] + __popc(s_bits[key >> 5] & ((1u << (key & 31)) - 1u));
+      l = (uint16_t)rank;
+      if (key == k * kTile + r) u[rank] = v;
     }
+    loc[k * kTile + r] = l;
   }
-  // amask: offsets with an entry anywhere in the tile (s_cnt holds the prefix, so compare neighbours)
   if (r == 0) {
     uint32_t am = 0;
-    for (int k = 0; k < K; ++k)
-      if (s_cnt[(k + 1) * 4] > s_cnt[k * 4]) am |= 1u << k;
-    meta[t] = make_int4((rec_hdr_bytes(K) + 3 * P + 15) & ~15, nU, (int)(am ? am : 1u), P);
-    atomicMax(stats, (rec_hdr_bytes(K) + 3 * P + 15) & ~15);  // largest record / most distinct rows of the map
+    int P = 0;
+    for (int k = 0; k < K; ++k) {
+      if (s_cnt[k] > 0) am |= 1u << k;
+      P += s_cnt[k];
+    }
+    if (am == 0) am = 1u;  // a tile without any entry still sends one all-lanes-off unit through the pipeline
+    *reinterpret_cast<uint4 *>(rec + 16 * K) = make_uint4((uint32_t)nU, am, (uint32_t)P, (uint32_t)__popc(am));
+    uint8_t *klist = rec + 16 * K + 16;
+    int n = 0;
+    for (uint32_t mm = am; mm; mm &= mm - 1) klist[n++] = (uint8_t)(__ffs(mm) - 1);
+    for (; n < 32; ++n) klist[n] = 0;
+    meta[t] = make_int4(rec_stride_bytes(K), nU, (int)am, P);
+    atomicMax(stats, P);  // most entries / most distinct rows of a tile of the map
     atomicMax(stats + 1, nU);
   }
 }
@@ -228,12 +242,9 @@ int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const
                reinterpret_cast<uintptr_t>(meta)) & 15) == 0,
              "tile_records: records/uidx/meta must be 16-byte aligned");
   const int HT = tile_table_slots(K);
-  size_t smem = ((size_t)K * kTile + 4 * K + 8 + HT) * sizeof(int32_t) + (size_t)K * kTile * sizeof(uint16_t);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    WSIS_CUDA(cudaFuncSetAttribute(tile_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  size_t smem = ((size_t)K * kTile + K + 8 + 2 * HT + 8 * K + 8) * sizeof(int32_t) + (size_t)K * kTile * sizeof(uint16_t);
+  // the opt-in is per device: set it on every call rather than caching it process-wide (multi-GPU processes)
+  WSIS_CUDA(cudaFuncSetAttribute(tile_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tile_record_kernel<<<(unsigned)n_tiles, kTile, smem, as_stream(stream)>>>(
       map, K, flip, HT, order, (uint8_t *)records, uidx, reinterpret_cast<int4 *>(meta), stats);
   WSIS_LAUNCH_OK();

@@ -98,7 +98,7 @@ def identity_order(n, device):
 
 
 class TileMap:
-    """A neighbour map in the form conv_umma consumes: destination rows in tiles of 128 along `order`, one compact
+    """A neighbour map in the form conv_umma consumes: destination rows in tiles of 128 along `order`, one
     record per tile (include/wsis_b200.h, wsis_tile_records)."""
 
     def __init__(self, map_, n_dst, flip, order):
@@ -108,7 +108,7 @@ class TileMap:
         self.num_tiles = lib().value("wsis_tile_pad", n_dst) // 128
         self.stride = lib().value("wsis_tile_record_stride", K)
         self.ustride = lib().value("wsis_tile_unique_stride", K)
-        # fixed-stride records (only the meaningful head of each is ever written or read): no size scan, no host sync
+        # fixed-stride records: no size scan, no host sync
         self.records = _bytes(self.num_tiles * self.stride, map_.device)
         self.uidx = torch.empty((max(self.num_tiles * self.ustride, 4),), dtype=torch.int32, device=map_.device)
         self.meta = torch.empty((max(self.num_tiles, 1), 4), dtype=torch.int32, device=map_.device)
@@ -116,10 +116,6 @@ class TileMap:
         if n_dst > 0:
             lib().call("wsis_tile_records", _ptr(map_), n_dst, K, int(flip), _ptr(order), _ptr(self.records),
                        _ptr(self.uidx), _ptr(self.meta), _ptr(self.stats), _stream())
-
-    # stats[0] (largest record of the map) could size the kernel's shared-memory record buffers; reading it back costs
-    # a host sync per tile map and more operand stages did not pay, so the worst case (0) is passed.
-    max_record_bytes = 0
 
 
 def _tiles_of(map_, n_dst, flip):
@@ -346,7 +342,7 @@ def sparse_conv(src, weight3, map_, n_dst, flip, transpose_w=False, prologue=Non
         tiles = tiles if tiles is not None else _tiles_of(map_, n_dst, int(flip))
         assert tiles.n_dst == n_dst and tiles.K == K
         lib().call("wsis_conv_umma", _ptr(src), _ptr(tiles.records), _ptr(tiles.uidx), _ptr(tiles.meta), _ptr(tiles.order),
-                   tiles.num_tiles, K, tiles.max_record_bytes, _ptr(buf), Cin, Cout, prec, _ptr(scale), _ptr(shift), int(relu), _ptr(residual),
+                   tiles.num_tiles, K, _ptr(buf), Cin, Cout, prec, _ptr(scale), _ptr(shift), int(relu), _ptr(residual),
                    _ptr(dst), _stream())
     else:
         lib().call("wsis_conv_simt", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(weight3), int(transpose_w), Cin,

@@ -119,16 +119,16 @@ int wsis_conv_simt(const float *src, const int32_t *map, int64_t n_dst, int K, i
  * wsis_tile_pad(n) = n rounded up to a multiple of 128.  wsis_spatial_order sorts a coordinate set along a
  * Morton curve (batch-major): order int32[wsis_tile_pad(N)] = row ids in curve order, padded with -1.
  * wsis_identity_order gives the trivial order for callers without coordinates.
- * wsis_tile_records compacts a neighbour map into per-tile RECORDS, the only form of the rulebook the tensor-core
+ * wsis_tile_records turns a neighbour map into per-tile RECORDS, the only form of the rulebook the tensor-core
  * kernel reads: for tile t (destination rows order[128t .. 128t+127]) and `m[r,k] = map[order[..], flip ? K-1-k : k]`
- *   records + t * wsis_tile_record_stride(K):
- *     valid[K][4] u32 | start[K+1] u16, nU u16 | eloc[P] u16 | eslot[P] u8          (P = pairs of the tile <= 128 K)
- *     entries of offset k are [start[k], start[k+1]); eloc = index of the entry's source row in the tile's list of
- *     DISTINCT source rows, eslot = tile slot (ascending inside an offset); valid[k] = slots that have an entry
+ *   records + t * wsis_tile_record_stride(K)   (stride = 16 K + 48 + 256 K bytes):
+ *     valid[K][4] u32 | {nU u32, amask u32, P u32, nact u32, klist u8[32]} | loc[K][128] u16
+ *     valid[k] = tile slots that have a source row through offset k; loc[k][r] = index of slot r's source row in the
+ *     tile's list of DISTINCT source rows (0xFFFF where the slot has none); amask = offsets with at least one entry
+ *     (1 if the tile has none at all), klist = those nact offsets in ascending order; P = entries of the tile
  *   uidx + t * wsis_tile_unique_stride(K): int32[nU] the distinct source rows of the tile (any order)
- *   meta[t] = int32[4] {meaningful record bytes, nU, mask of offsets with an entry (1 if none at all), P}
- *   stats = int32[2] {largest meaningful record bytes, largest nU} over the tiles (lets the conv kernel size its
- *   shared-memory record buffers for this map instead of the worst case)
+ *   meta[t] = int32[4] {record bytes, nU, amask, P}
+ *   stats = int32[2] {largest P, largest nU} over the tiles
  * records: uint8[num_tiles * stride], uidx: int32[num_tiles * unique_stride], meta: int32[num_tiles * 4], all 16-byte
  * aligned.  K <= 32. */
 int64_t wsis_tile_pad(int64_t n);
@@ -143,28 +143,29 @@ int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const
 
 /* tcgen05 tensor-core path over tile records (num_tiles = wsis_tile_pad(n_dst)/128).  precision: 1 = bf16 operands
  * (1e-2 contract), 3 = bf16x3 split operands with fp32 accumulation in TMEM (1e-4 contract).
- * Requires Cout % 16 == 0, 16 <= Cout <= 256, K <= 32; any Cin (channels are zero-padded to a multiple of 32 inside
- * the kernel and in the packed weights; rows are read with 16-byte loads when Cin % 4 == 0 and src is aligned).
- * max_record_bytes = stats[0] of wsis_tile_records when the caller has read it back, else 0 (worst case: fewer
- * pipeline stages fit in shared memory). */
+ * Requires Cout % 16 == 0, 16 <= Cout <= 256, K <= 32; any Cin (channels are zero-padded to a multiple of the unit
+ * width inside the kernel and in the packed weights; rows are read with 16-byte loads when Cin % 4 == 0 and src is
+ * aligned). */
 int wsis_conv_umma_supported(int Cin, int Cout);
 int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision);
 int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
                            wsis_stream_t stream);
-/* Launch plan of a layer shape (pure host arithmetic, no device needed): plan = int32[8] {dynamic shared-memory bytes,
- * pipeline stages, row-cache buffers, record buffers, builder stage owners, TMEM accumulators, MMA issuers, TMEM columns}.
- * Fails when no pipeline fits the 227 KB of shared memory. */
-int wsis_conv_umma_plan(int K, int Cin, int Cout, int precision, int max_record_bytes, int32_t *plan);
+/* Launch plan of a layer shape (pure host arithmetic, no device needed): plan = int32[10] {dynamic shared-memory
+ * bytes, pipeline stages, row-cache buffers, record buffers, builder groups, TMEM accumulators, MMA issuers,
+ * accumulator buffers (1|2), weights resident in shared memory (0|1), weight-producer warps}.
+ * Fails when no pipeline fits the 227 KB of shared memory / 512 TMEM columns. */
+int wsis_conv_umma_plan(int K, int Cin, int Cout, int precision, int32_t *plan);
 int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, const int32_t *meta,
-                   const int32_t *order, int64_t num_tiles, int K, int max_record_bytes, const void *packed, int Cin,
-                   int Cout, int precision,
+                   const int32_t *order, int64_t num_tiles, int K, const void *packed, int Cin, int Cout, int precision,
                    const float *in_scale, const float *in_shift, int in_relu, const float *residual, float *dst,
                    wsis_stream_t stream);
 
-/* Diagnostics: when buf != NULL, CTA 0 of every following wsis_conv_umma launch appends (globaltimer ns, event code)
- * pairs of its first tiles to buf = uint64[2 * capacity], capacity >= 32 * 512 (one 512-entry region per role; zero it
- * first, entries with time 0 are unused).  NULL disables. */
-int wsis_conv_debug_timeline(void *buf, int capacity);
+/* Diagnostics: when buf != NULL, every following wsis_conv_umma launch runs the instrumented build of the kernel and
+ * CTA 0 writes, for each of its 23 warps w, buf[8 w + 0] = cycles in the role loop and buf[8 w + 1..4] = cycles spent in
+ * the role's barrier waits (epilogue: accumulator full; gatherers: record, row-cache free; builders: record, row cache
+ * full, operand slot free; issuers: record, accumulator free, stage full; record producer: buffer free; weight
+ * producers: stage free).  buf = int64[23 * 8] device memory.  NULL switches back to the product kernel. */
+int wsis_conv_debug_stats(void *buf);
 
 /* dW[k] = sum_r prologue(src[map[r,k']])^T . g[r]   (fp32, dW is zeroed by the call). */
 int wsis_conv_wgrad(const float *src, const int32_t *map, int64_t n_dst, int K, int flip, const float *g, int Cin,

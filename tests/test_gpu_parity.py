@@ -535,28 +535,26 @@ def _decode_records(t, K):
     rec = t.records.cpu().numpy()
     meta = t.meta.cpu().numpy()
     uidx = t.uidx.cpu().numpy()
-    hdr = 16 * K + ((2 * (K + 2) + 15) // 16) * 16
+    assert t.stride == 16 * K + 48 + 256 * K
     out = np.full((t.num_tiles * 128, K), -1, np.int32)
     for ti in range(t.num_tiles):
         r = rec[ti * t.stride:(ti + 1) * t.stride]
         valid = r[:16 * K].view(np.uint32).reshape(K, 4)
-        start = r[16 * K:16 * K + 2 * (K + 2)].view(np.uint16).astype(np.int64)
-        P, nU = int(start[K]), int(start[K + 1])
-        amask = sum(1 << k for k in range(K) if start[k + 1] > start[k]) or 1
-        assert list(meta[ti]) == [(hdr + 3 * P + 15) // 16 * 16, nU, amask, P]
-        assert start[0] == 0 and np.all(np.diff(start[:K + 1]) >= 0)
+        hdr = r[16 * K:16 * K + 16].view(np.uint32)
+        nU, amask, P, nact = int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[3])
+        klist = r[16 * K + 16:16 * K + 48]
+        assert [int(k) for k in klist[:nact]] == [k for k in range(K) if amask >> k & 1] and nact == bin(amask).count("1")
+        loc = r[16 * K + 48:].view(np.uint16).reshape(K, 128).astype(np.int64)
+        bits = np.unpackbits(valid.view(np.uint8).reshape(K, 16), axis=1, bitorder="little").astype(bool)
+        assert P == bits.sum() and amask == (sum(1 << k for k in range(K) if bits[k].any()) or 1)
+        assert list(meta[ti]) == [t.stride, nU, amask, P]
         uniq = uidx[ti * t.ustride:ti * t.ustride + nU]
         assert len(np.unique(uniq)) == nU                      # the tile's source rows, each exactly once
-        loc = r[hdr:hdr + 2 * P].view(np.uint16).astype(np.int64)
-        slot = r[hdr + 2 * P:hdr + 3 * P]
-        assert P == 0 or (loc.max() < nU and len(np.unique(loc)) == nU)
+        assert P == 0 or (loc[bits].max() < nU and len(np.unique(loc[bits])) == nU)
+        assert np.all(loc[~bits] == 0xFFFF)
         for k in range(K):
-            sl = slot[start[k]:start[k + 1]].astype(np.int64)
-            assert np.all(np.diff(sl) > 0)
-            bits = np.zeros(128, bool)
-            bits[sl] = True
-            assert np.array_equal(np.unpackbits(valid[k].view(np.uint8), bitorder="little").astype(bool), bits)
-            out[ti * 128 + sl, k] = uniq[loc[start[k]:start[k + 1]]]
+            sl = np.nonzero(bits[k])[0]
+            out[ti * 128 + sl, k] = uniq[loc[k, sl]]
     return out
 
 

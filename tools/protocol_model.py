@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """Executable model of the mbarrier protocol of conv_umma_kernel (3d-wsis_b200/csrc/conv_umma.cu).
 
-The kernel is nine cooperating loops (record producer, weight producer, gather warps, builder warps, MMA issuers,
-epilogue warps) that hand shared-memory buffers to each other through mbarriers whose waits only test a PARITY bit.
-A parity wait is sound only while the waiter can never be two phases away from the phase it means; one version of
-the kernel violated that (more builder warps than operand stages) and hung on the GPU.  This model transcribes the
-control flow of every role -- the same ring indices, the same parities, the same arrival counts -- and runs the
-roles under a random scheduler while checking, at every wait that passes, that the LOGICAL generation the waiter
-needs has really completed, and at every buffer use that the buffer holds what the consumer expects.  A violation
-or a deadlock raises.  tests/test_cpu.py runs it over every launch plan wsis_conv_umma_plan can produce.
+The kernel is a set of cooperating loops (record producer, weight producers, gather warps, builder groups, MMA
+issuers, epilogue warps) that hand shared-memory / tensor-memory buffers to each other through mbarriers whose waits
+only test a PARITY bit.  A parity wait is sound only while the waiter can never be two phases away from the phase it
+means; one version of the kernel violated that (more builder warps than operand stages) and hung on the GPU.  This
+model transcribes the control flow of every role -- the same ring indices, the same parities, the same arrival
+counts -- and runs the roles under a random scheduler while checking, at every wait that passes, that the LOGICAL
+generation the waiter needs has really completed, and at every buffer use that the buffer holds what the consumer
+expects.  A violation or a deadlock raises.  tests/test_cpu.py runs it over every launch plan wsis_conv_umma_plan
+can produce.
 
     python tools/protocol_model.py            # quick self-check
 """
@@ -45,21 +46,22 @@ def wait(bar, parity, needed_phases, what):
 class Cta(object):
     """One persistent CTA working through `tiles` = list of (number of active offsets, KB)."""
 
-    def __init__(self, tiles, na, nrc, nrec, nb, nmma, builder_halves=2, gather_warps=4, epi_warps=4):
+    def __init__(self, tiles, na, nrc, nrec, nbg, nmma, nbuf=2, resident=False, nwp=2, gather_warps=4, epi_warps=4):
         assert na & (na - 1) == 0
-        self.tiles, self.na, self.nrc, self.nrec, self.nb, self.nmma = tiles, na, nrc, nrec, nb, nmma
-        self.halves, self.G, self.E = builder_halves, gather_warps, epi_warps
+        self.tiles, self.na, self.nrc, self.nrec, self.nbg, self.nmma = tiles, na, nrc, nrec, nbg, nmma
+        self.nbuf, self.resident, self.nwp = nbuf, resident, nwp
+        self.G, self.E = gather_warps, epi_warps
         self.lna = na.bit_length() - 1
-        self.afull = [Barrier(builder_halves + 1) for _ in range(na)]      # builders + weight producer (expect_tx)
+        self.afull = [Barrier(4 + (0 if resident else 1)) for _ in range(na)]  # 4 builder warps (+ weight expect_tx)
         self.aempty = [Barrier(1) for _ in range(na)]                      # tcgen05.commit
         self.rcf = [Barrier(gather_warps) for _ in range(nrc)]
-        self.rce = [Barrier(builder_halves * nb) for _ in range(nrc)]
+        self.rce = [Barrier(4 * nbg) for _ in range(nrc)]
         self.recf = [Barrier(1) for _ in range(nrec)]
-        self.rece = [Barrier(gather_warps + builder_halves * nb) for _ in range(nrec)]
+        self.rece = [Barrier(gather_warps + 4 * nbg + nmma) for _ in range(nrec)]
         self.accf = [Barrier(nmma) for _ in range(2)]
         self.acce = [Barrier(epi_warps) for _ in range(2)]
         # buffer contents (what the consumer must find)
-        self.stage_rows = [[None] * builder_halves for _ in range(na)]     # unit id written by each builder half
+        self.stage_rows = [[None] * 4 for _ in range(na)]                  # unit id written by each builder warp
         self.stage_w = [None] * na                                         # unit id of the weight block
         self.rc = [None] * nrc                                             # pass id
         self.rec = [None] * nrec                                           # tile iteration
@@ -75,15 +77,18 @@ class Cta(object):
             yield
             self.recf[rb].arrive()                                         # expect_tx arrive + bytes landed
 
-    def weight_producer(self):
+    def weight_producer(self, wi):
+        if self.resident:
+            return
         j = 0
         for nact, KB in self.tiles:
             for _ in range(KB * nact):
-                s = j & (self.na - 1)
-                yield from wait(self.aempty[s], ((j >> self.lna) & 1) ^ 1, j >> self.lna, "weight slot free")
-                self.stage_w[s] = j
-                yield
-                self.afull[s].arrive()
+                if j % self.nwp == wi:
+                    s = j & (self.na - 1)
+                    yield from wait(self.aempty[s], ((j >> self.lna) & 1) ^ 1, j >> self.lna, "weight slot free")
+                    self.stage_w[s] = j
+                    yield
+                    self.afull[s].arrive()
                 j += 1
 
     def gatherer(self, g):
@@ -105,10 +110,8 @@ class Cta(object):
             self.rece[rb].arrive()
 
     def builder(self, bw):
-        b, half = bw % self.nb, bw // self.nb
-        if half >= self.halves:
-            return
-        q = j0 = 0
+        g, w4 = bw // 4, bw % 4
+        q = j = 0
         for it, (nact, KB) in enumerate(self.tiles):
             rb = it % self.nrec
             yield from wait(self.recf[rb], (it // self.nrec) & 1, it // self.nrec + 1, "record ready (builder)")
@@ -117,53 +120,56 @@ class Cta(object):
             for kb in range(KB):
                 slot = q % self.nrc
                 yield from wait(self.rcf[slot], (q // self.nrc) & 1, q // self.nrc + 1, "row cache full")
-                jb = j0 + kb * nact
-                ak = (b + self.nb - jb % self.nb) % self.nb
-                while ak < nact:
-                    j = jb + ak
-                    stage, phase = j & (self.na - 1), (j >> self.lna) & 1
-                    if self.rc[slot] != q:
-                        raise ProtocolError("builder reads row cache of pass %s, wants %d" % (self.rc[slot], q))
-                    yield                                                   # prefetch rows into registers
-                    yield from wait(self.aempty[stage], phase ^ 1, j >> self.lna, "operand stage free")
-                    self.stage_rows[stage][half] = j
-                    yield
-                    self.afull[stage].arrive()
-                    ak += self.nb
+                for _ in range(nact):
+                    if j % self.nbg == g:
+                        stage, phase = j & (self.na - 1), (j >> self.lna) & 1
+                        if self.rc[slot] != q:
+                            raise ProtocolError("builder reads row cache of pass %s, wants %d" % (self.rc[slot], q))
+                        yield                                               # rows -> registers
+                        yield from wait(self.aempty[stage], phase ^ 1, j >> self.lna, "operand slot free")
+                        self.stage_rows[stage][w4] = j
+                        yield
+                        self.afull[stage].arrive()
+                    j += 1
                 self.rce[slot].arrive()
                 q += 1
-            j0 += nact * KB
             self.rece[rb].arrive()
 
     def issuer(self, mi):
-        j0 = 0
+        j = 0
+        acc, aph = 0, 0
         for it, (nact, KB) in enumerate(self.tiles):
-            n, acc = nact * KB, it & 1
-            yield from wait(self.acce[acc], ((it >> 1) & 1) ^ 1, it >> 1, "accumulator free")
-            u = (mi - j0) & (self.nmma - 1)
-            while u < n:
-                j = j0 + u
-                sa = j & (self.na - 1)
-                yield from wait(self.afull[sa], (j >> self.lna) & 1, (j >> self.lna) + 1, "stage full")
-                if self.stage_w[sa] != j or any(r != j for r in self.stage_rows[sa]):
-                    raise ProtocolError("issuer %d, unit %d: stage holds rows %s weights %s"
-                                        % (mi, j, self.stage_rows[sa], self.stage_w[sa]))
-                if self.acc_tile[acc] not in (None, it):
-                    raise ProtocolError("accumulator %d still holds tile %s" % (acc, self.acc_tile[acc]))
-                self.acc_tile[acc] = it
-                yield                                                       # MMAs execute
-                self.done_units.append(j)
-                self.aempty[sa].arrive()                                    # tcgen05.commit
-                u += self.nmma
-            j0 += n
+            rb = it % self.nrec
+            yield from wait(self.recf[rb], (it // self.nrec) & 1, it // self.nrec + 1, "record ready (issuer)")
+            if self.rec[rb] != it:
+                raise ProtocolError("issuer reads record of tile %s, wants %d" % (self.rec[rb], it))
+            yield from wait(self.acce[acc], aph ^ 1, it // self.nbuf, "accumulator free")
+            for _ in range(nact * KB):
+                if j & (self.nmma - 1) == mi:
+                    sa = j & (self.na - 1)
+                    yield from wait(self.afull[sa], (j >> self.lna) & 1, (j >> self.lna) + 1, "stage full")
+                    if (not self.resident and self.stage_w[sa] != j) or any(r != j for r in self.stage_rows[sa]):
+                        raise ProtocolError("issuer %d, unit %d: stage holds rows %s weights %s"
+                                            % (mi, j, self.stage_rows[sa], self.stage_w[sa]))
+                    if self.acc_tile[acc] not in (None, it):
+                        raise ProtocolError("accumulator %d still holds tile %s" % (acc, self.acc_tile[acc]))
+                    self.acc_tile[acc] = it
+                    yield                                                   # MMAs execute
+                    self.done_units.append(j)
+                    self.aempty[sa].arrive()                                # tcgen05.commit
+                j += 1
             yield
             self.accf[acc].arrive()
+            self.rece[rb].arrive()
+            acc += 1
+            if acc == self.nbuf:
+                acc, aph = 0, aph ^ 1
 
     def epilogue(self, w):
+        acc, aph = 0, 0
         for it in range(len(self.tiles)):
-            acc = it & 1
-            yield from wait(self.accf[acc], (it >> 1) & 1, (it >> 1) + 1, "accumulator full")
-            if self.acc_tile[acc] != it:
+            yield from wait(self.accf[acc], aph, it // self.nbuf + 1, "accumulator full")
+            if self.acc_tile[acc] not in (it, None):                        # None: a tile whose units all went elsewhere
                 raise ProtocolError("epilogue reads tile %s, wants %d" % (self.acc_tile[acc], it))
             yield
             if w == 0:
@@ -171,12 +177,15 @@ class Cta(object):
             self.acce[acc].arrive()
             if self.acce[acc].pending == self.acce[acc].count:              # last warp released the buffer
                 self.acc_tile[acc] = None
+            acc += 1
+            if acc == self.nbuf:
+                acc, aph = 0, aph ^ 1
 
     def run(self, seed=0, max_steps=10 ** 7):
         rng = random.Random(seed)
-        roles = [self.record_producer(), self.weight_producer()]
+        roles = [self.record_producer()] + [self.weight_producer(w) for w in range(self.nwp)]
         roles += [self.gatherer(g) for g in range(self.G)]
-        roles += [self.builder(b) for b in range(self.halves * self.nb)]
+        roles += [self.builder(b) for b in range(4 * self.nbg)]
         roles += [self.issuer(m) for m in range(self.nmma)]
         roles += [self.epilogue(w) for w in range(self.E)]
         alive = list(range(len(roles)))
@@ -213,13 +222,14 @@ def random_tiles(rng, n_tiles, max_units=27, max_kb=3):
 
 if __name__ == "__main__":
     r = random.Random(1)
-    for na, nrc, nb, nmma in ((4, 3, 4, 2), (8, 3, 4, 2), (2, 2, 2, 2), (1, 1, 1, 1), (4, 2, 4, 1)):
+    for na, nrc, nbg, nmma, nbuf, res in ((8, 3, 2, 4, 2, True), (8, 3, 2, 2, 2, False), (4, 2, 2, 1, 2, False),
+                                          (8, 2, 2, 1, 1, False), (2, 1, 2, 1, 2, False), (4, 2, 2, 4, 2, False)):
         for seed in range(20):
-            Cta(random_tiles(r, 6), na, nrc, 2, nb, nmma).run(seed)
+            Cta(random_tiles(r, 6), na, nrc, 2, nbg, nmma, nbuf=nbuf, resident=res).run(seed)
     print("protocol ok")
-    try:  # the configuration that hung on the GPU: 6 single-warp builders on 4 stages
+    try:  # four issuers on a two-stage ring: an issuer's next unit is two generations ahead on the same stage
         for seed in range(50):
-            Cta(random_tiles(r, 6), 4, 3, 2, 6, 2, builder_halves=1).run(seed)
-        print("(the nb > na configuration was not caught)")
+            Cta(random_tiles(r, 6), 2, 2, 2, 2, 4).run(seed)
+        print("(the nmma > na configuration was not caught)")
     except ProtocolError as e:
-        print("nb > na is caught:", e)
+        print("nmma > na is caught:", e)
