@@ -56,11 +56,13 @@ constexpr int kEpiWarps = 4, kGatherWarps = 4, kBuildGroups = 2, kBuildWarps = 4
               kRecWarps = 1, kWgtWarps = 2;
 constexpr int kGatherWarp0 = kEpiWarps, kBuildWarp0 = kGatherWarp0 + kGatherWarps, kMmaWarp0 = kBuildWarp0 + kBuildWarps,
               kRecWarp0 = kMmaWarp0 + kMmaWarps, kWgtWarp0 = kRecWarp0 + kRecWarps;
-constexpr int kThreads = (kWgtWarp0 + kWgtWarps) * 32;  // 736
+constexpr int kThreads = 768;  // six warpgroups; the last warp of the producers' group is idle
+static_assert((kWgtWarp0 + kWgtWarps) * 32 <= kThreads && kMmaWarp0 % 4 == 0 && kRecWarp0 % 4 == 0, "roles are laid out in whole warpgroups");
 static_assert(kBuildWarp0 % 4 == 0, "a builder warp must own TMEM lanes 32 * (warp % 4)");
 constexpr int kRcap = 256;    // rows of one row-cache buffer (a surface tile reads ~160-230 distinct rows)
 constexpr int kRowB = 128;    // bytes of one converted row: 32 ch x (hi, mid) or 64 ch x bf16
-constexpr int kRcBuf = kRcap * kRowB;
+constexpr int kRowStride = 144;  // row-cache row pitch: 128 + 16 bytes of padding (see rc layout below)
+constexpr int kRcBuf = kRcap * kRowStride;
 constexpr int kSlotCols = 32;  // TMEM columns of one operand slot (128 B per lane)
 constexpr int kResidentBytes = 112 * 1024;  // packed weights up to this size stay in shared memory for the whole launch
 
@@ -80,9 +82,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // NANOSLEEP.SYNCS after a failed probe and the wake-up latency of a sleeping warp (on both sides of every stage hand-off)
 // dominated the pipeline's round trip.  A wait that has not completed after ~4 s is a protocol bug: report which
 // barrier and trap instead of hanging the device.
-__device__ __noinline__ void mbar_deadlock(uint32_t bar, uint32_t parity) {
-  printf("wsis conv_umma: barrier wait timed out: block %d warp %d lane %d barrier@%u parity %u\n", (int)blockIdx.x,
-         (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), bar, parity);
+__device__ __forceinline__ void mbar_deadlock(uint32_t bar, uint32_t parity) {
+  // no printf here: a device-side call would force the ABI on the kernel, and setmaxnreg needs a call-free kernel.
+  // The trap surfaces as a launch failure on the next CUDA call; WSIS_CONV_DIAG builds report which barrier.
+  (void)bar;
+  (void)parity;
   __trap();
 }
 // The wait loop is written in PTX so that one failed probe costs ~3 issue slots (try_wait + branch, the watchdog count
@@ -118,7 +122,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // Waits that are not on the unit pipeline's critical path (the epilogue waits several microseconds for a tile, the
 // record producer for a free buffer) let the warp sleep between probes: a sleeping warp costs no issue slots.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns = 2000) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns = 600) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -126,8 +130,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
       ".reg .u32 n;\n"
       "mov.u32 n, 0;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "@p bra LAB_DONE;\n"
+      "nanosleep.u32 %3;\n"
       "add.u32 n, n, 1;\n"
       "setp.lt.u32 q, n, 4194304;\n"
       "@q bra LAB_WAIT;\n"
@@ -140,35 +145,33 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
   if (!ok) mbar_deadlock(bar, parity);
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // In-order issue means a warp stalls at the first instruction that needs the probe's result (~90 cycles even when the
 // barrier has already flipped).  These two forms put independent shared-memory loads between the first probe and the
 // branch that consumes it, so the probe's latency and the loads' latency overlap.
 //   rows: v[0..7] <- 8 x 16 bytes at rbase + ((c ^ f) << 4) when `has` (other lanes keep their registers)
 __device__ __forceinline__ void mbar_wait_and_load_row(uint32_t bar, uint32_t parity, uint4 (&v)[8], uint32_t rbase,
-                                                       uint32_t fx16, uint32_t has) {
+                                                       uint32_t has) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p, q, h;\n"
-      ".reg .u32 n, a;\n"
-      "setp.ne.u32 h, %37, 0;\n"
+      ".reg .u32 n;\n"
+      "setp.ne.u32 h, %36, 0;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%33], %34;\n"
-      "add.u32 a, %35, %36;\n"
-      "@h ld.shared.v4.u32 {%1,%2,%3,%4}, [a];\n"
-      "xor.b32 a, %36, 0x10;\n add.u32 a, a, %35;\n"
-      "@h ld.shared.v4.u32 {%5,%6,%7,%8}, [a];\n"
-      "xor.b32 a, %36, 0x20;\n add.u32 a, a, %35;\n"
-      "@h ld.shared.v4.u32 {%9,%10,%11,%12}, [a];\n"
-      "xor.b32 a, %36, 0x30;\n add.u32 a, a, %35;\n"
-      "@h ld.shared.v4.u32 {%13,%14,%15,%16}, [a];\n"
-      "xor.b32 a, %36, 0x40;\n add.u32 a, a, %35;\n"
-      "@h ld.shared.v4.u32 {%17,%18,%19,%20}, [a];\n"
-      "xor.b32 a, %36, 0x50;\n add.u32 a, a, %35;\n"
-      "@h ld.shared.v4.u32 {%21,%22,%23,%24}, [a];\n"
-      "xor.b32 a, %36, 0x60;\n add.u32 a, a, %35;\n"
-      "@h ld.shared.v4.u32 {%25,%26,%27,%28}, [a];\n"
-      "xor.b32 a, %36, 0x70;\n add.u32 a, a, %35;\n"
-      "@h ld.shared.v4.u32 {%29,%30,%31,%32}, [a];\n"
+      "@h ld.shared.v4.u32 {%1,%2,%3,%4}, [%35];\n"
+      "@h ld.shared.v4.u32 {%5,%6,%7,%8}, [%35+16];\n"
+      "@h ld.shared.v4.u32 {%9,%10,%11,%12}, [%35+32];\n"
+      "@h ld.shared.v4.u32 {%13,%14,%15,%16}, [%35+48];\n"
+      "@h ld.shared.v4.u32 {%17,%18,%19,%20}, [%35+64];\n"
+      "@h ld.shared.v4.u32 {%21,%22,%23,%24}, [%35+80];\n"
+      "@h ld.shared.v4.u32 {%25,%26,%27,%28}, [%35+96];\n"
+      "@h ld.shared.v4.u32 {%29,%30,%31,%32}, [%35+112];\n"
       "mov.u32 n, 0;\n"
       "@p bra LAB_DONE;\n"
       "LAB_WAIT:\n"
@@ -187,9 +190,30 @@ __device__ __forceinline__ void mbar_wait_and_load_row(uint32_t bar, uint32_t pa
         "+r"(v[3].w), "+r"(v[4].x), "+r"(v[4].y), "+r"(v[4].z), "+r"(v[4].w), "+r"(v[5].x), "+r"(v[5].y), "+r"(v[5].z),
         "+r"(v[5].w), "+r"(v[6].x), "+r"(v[6].y), "+r"(v[6].z), "+r"(v[6].w), "+r"(v[7].x), "+r"(v[7].y), "+r"(v[7].z),
         "+r"(v[7].w)
-      : "r"(bar), "r"(parity), "r"(rbase), "r"(fx16), "r"(has)
+      : "r"(bar), "r"(parity), "r"(rbase), "r"(has)
       : "memory");
   if (!ok) mbar_deadlock(bar, parity);
+}
+__device__ __forceinline__ void load_row(uint4 (&v)[8], uint32_t rbase, uint32_t has) {
+  asm volatile(
+      "{\n"
+      ".reg .pred h;\n"
+      "setp.ne.u32 h, %33, 0;\n"
+      "@h ld.shared.v4.u32 {%0,%1,%2,%3}, [%32];\n"
+      "@h ld.shared.v4.u32 {%4,%5,%6,%7}, [%32+16];\n"
+      "@h ld.shared.v4.u32 {%8,%9,%10,%11}, [%32+32];\n"
+      "@h ld.shared.v4.u32 {%12,%13,%14,%15}, [%32+48];\n"
+      "@h ld.shared.v4.u32 {%16,%17,%18,%19}, [%32+64];\n"
+      "@h ld.shared.v4.u32 {%20,%21,%22,%23}, [%32+80];\n"
+      "@h ld.shared.v4.u32 {%24,%25,%26,%27}, [%32+96];\n"
+      "@h ld.shared.v4.u32 {%28,%29,%30,%31}, [%32+112];\n"
+      "}\n"
+      : "+r"(v[0].x), "+r"(v[0].y), "+r"(v[0].z), "+r"(v[0].w), "+r"(v[1].x), "+r"(v[1].y), "+r"(v[1].z), "+r"(v[1].w),
+        "+r"(v[2].x), "+r"(v[2].y), "+r"(v[2].z), "+r"(v[2].w), "+r"(v[3].x), "+r"(v[3].y), "+r"(v[3].z), "+r"(v[3].w),
+        "+r"(v[4].x), "+r"(v[4].y), "+r"(v[4].z), "+r"(v[4].w), "+r"(v[5].x), "+r"(v[5].y), "+r"(v[5].z), "+r"(v[5].w),
+        "+r"(v[6].x), "+r"(v[6].y), "+r"(v[6].z), "+r"(v[6].w), "+r"(v[7].x), "+r"(v[7].y), "+r"(v[7].z), "+r"(v[7].w)
+      : "r"(rbase), "r"(has)
+      : "memory");
 }
 //   mask: m <- 16 bytes at maddr (the issuer's disable-output-lane mask of the unit)
 __device__ __forceinline__ void mbar_wait_and_load16(uint32_t bar, uint32_t parity, uint4 &m, uint32_t maddr) {
@@ -324,11 +348,9 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __host__ __device__ __forceinline__ uint32_t sw64(uint32_t row, uint32_t c16) {
   return (row >> 3) * 512u + (row & 7u) * 64u + ((c16 ^ ((row & 7u) >> 1)) << 4);
 }
-// Row cache: row u is 128 B = 8 chunks of 16 B; logical chunk c lives at chunk c ^ rc_swz(u).  Builder lanes read
-// the SAME logical chunk of DIFFERENT rows (one 8-lane phase per quarter warp): rows whose indices differ in their low
-// three bits land in different bank groups.  Bit 0 of u flips the 64-byte half, so that the gatherers, who write 64
-// contiguous bytes (hi) of consecutive rows in one half-warp, do not collide either.
-__device__ __forceinline__ uint32_t rc_swz(uint32_t u) { return ((u & 1u) << 2) | ((u >> 1) & 3u); }
+// Row cache: row u is 8 chunks of 16 B at pitch 144 B, so chunk c of row u sits in shared-memory bank group
+// (u + c) mod 8.  Builder lanes read the SAME chunk of DIFFERENT rows: rows whose indices differ in their low three bits
+// land in different bank groups, and all eight chunks of a row are base + immediate offsets (no per-chunk address math).
 
 struct Params {
   const float *src;
@@ -340,6 +362,7 @@ struct Params {
   const float *in_scale, *in_shift, *residual;
   float *dst;
   int K, Cin, Cout, KB, in_relu, vec4;
+  int us;  // units (offset x channel block) per pipeline stage, 1..4
   int lna, nrc, nrec, nacc, nmma, nbuf, resident, nwp;  // 1 << lna pipeline stages, nrc row-cache buffers, nrec record
                                                         // buffers, accumulators (= issuers), accumulator buffers (1|2),
                                                         // weights resident in shared memory, weight-producer warps
@@ -382,7 +405,7 @@ __device__ __forceinline__ float4 prologue4(float4 x, float4 sc, float4 sh, int 
 
 // A tile that reads more distinct rows than a row-cache buffer holds fetches the overflow rows directly: 8 channels
 // [c0, c0 + 8) of unique row `loc` of the tile -> prologue -> 8 bf16 (hi or mid).  Rare; kept out of line.
-__device__ __noinline__ uint4 fetch_direct(const float *src, int Cin, int vec4, int in_relu, const int32_t *urows,
+__device__ __forceinline__ uint4 fetch_direct(const float *src, int Cin, int vec4, int in_relu, const int32_t *urows,
                                            uint32_t loc, int c0, int part, const float *s_scale, const float *s_shift) {
   const int32_t row = __ldg(urows + loc);
   const float4 y0 = prologue4(load_row4(src, Cin, vec4, row, c0), *reinterpret_cast<const float4 *>(s_scale + c0),
@@ -408,11 +431,6 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
 
 // NS = 2: fp32 contract (hi + mid, 32 channels per unit); NS = 1: bf16 operands (64 channels per unit)
 template <int NS, bool DIAG>
@@ -428,7 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t w_stage = 2 * b_block;             // (hi, mid) of 32 channels, or two 32-channel halves of bf16
   const uint32_t rec_main = (uint32_t)rec_stride_bytes(p.K);
   const uint32_t rec_buf = rec_main + kRcap * 4;  // record + the first kRcap unique rows
-  const uint32_t w_bytes = p.resident ? (uint32_t)(p.K * KB) * w_stage : na * w_stage;
+  const uint32_t us = (uint32_t)p.us;  // units per stage
+  const uint32_t w_bytes = p.resident ? (uint32_t)(p.K * KB) * w_stage : na * us * w_stage;
   uint8_t *s_w = sm;                                   // weight blocks: ring of na stages, or the whole packed weight
   uint8_t *s_rc = s_w + w_bytes;                       // [nrc][kRcap][128 B]   converted source rows
   uint8_t *s_rec = s_rc + (size_t)p.nrc * kRcBuf;      // [nrec][rec_buf]       tile records (bulk copies)
@@ -453,6 +472,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long dg[4] = {0, 0, 0, 0};
   const long long dg_t0 = DIAG ? clock64() : 0;
+  int tl_n = 0;  // timeline of CTA 0 (diagnostics build): p.diag[256 + warp * 512 + n] = cycles since start << 8 | code
+#define TL(code)                                                                                   \
+  do {                                                                                             \
+    if (DIAG && p.diag != nullptr && blockIdx.x == 0 && lane == 0 && tl_n < 512)                   \
+      p.diag[256 + warp * 512 + tl_n++] = ((clock64() - dg_t0) << 8) | (long long)((code) & 0xff); \
+  } while (0)
 #define WAIT(i, bar, parity) mbar_wait_t<DIAG>(bar, parity, dg[i], (uint32_t)p.wait_ns)
 #define WAIT_RELAXED(i, bar, parity) mbar_wait_t<DIAG, true>(bar, parity, dg[i], 0u)
 
@@ -514,6 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
 
   if (warp < kEpiWarps) {
     // ===================== epilogue: TMEM -> registers -> (+residual) -> global, once per tile =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");
     // Everything that does not depend on the accumulator is in flight before the wait: the tile's destination rows
     // (fetched one tile ahead) and the residual of the first 16-column chunk; inside the tile the residual of chunk
     // c + 1 is fetched while chunk c is read out of TMEM.
@@ -530,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
 #pragma unroll
       for (int q = 0; q < 4; ++q) r4[q] = has_res ? __ldg(rs + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       WAIT_RELAXED(0, accf_bar(as), aph);
+      TL(1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * acc_cols;
       for (int c0 = 0; c0 < p.Cout && !(p.dbg & 16); c0 += 16) {
@@ -561,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(acce_bar(as));
+      TL(2);
       if (++as == (uint32_t)p.nbuf) {
         as = 0;
         aph ^= 1;
@@ -568,6 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     }
   } else if (warp < kBuildWarp0) {
     // ===================== gatherers: every distinct source row of a tile is fetched ONCE =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;" ::: "memory");
     // One PASS = (tile, channel block kb): the slices of the tile's unique rows are loaded with 16-byte loads
     // (8 rows per lane in flight), the fused eval-BatchNorm+ReLU prologue is applied, the result is split
     // fp32 -> bf16 hi (+ bf16 mid) and parked in a row-cache buffer, from which the builders assemble the per-offset
@@ -579,7 +608,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     uint32_t it = 0, q = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t rb = it % p.nrec;
-      WAIT(0, recf_bar(rb), (it / p.nrec) & 1);
+      WAIT_RELAXED(0, recf_bar(rb), (it / p.nrec) & 1);
+      TL(3);
       const uint8_t *rec = s_rec + (size_t)rb * rec_buf;
       // distinct rows of the tile (the overflow beyond a row-cache buffer is fetched directly by the builders)
       const int ng = min((int)*reinterpret_cast<const uint32_t *>(rec + 16 * p.K), kRcap);
@@ -615,37 +645,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
             const int u = u0 + i * kSweep + rsub;
             if (u < ng) {
               const float4 y = prologue4(v[i], sc, sh, p.in_relu);
-              const uint32_t f = rc_swz((uint32_t)u);
-              uint8_t *r = rcb + (size_t)u * kRowB + (chunk & 1) * 8;
-              *reinterpret_cast<uint2 *>(r + ((((uint32_t)chunk >> 1) ^ f) << 4)) =
-                  make_uint2(split2(y.x, y.y, 0), split2(y.z, y.w, 0));
-              if (NS == 2)
-                *reinterpret_cast<uint2 *>(r + (((((uint32_t)chunk >> 1) + 4u) ^ f) << 4)) =
-                    make_uint2(split2(y.x, y.y, 1), split2(y.z, y.w, 1));
+              uint8_t *r = rcb + (size_t)u * kRowStride + chunk * 8;  // 16-byte chunk (chunk >> 1), half (chunk & 1)
+              *reinterpret_cast<uint2 *>(r) = make_uint2(split2(y.x, y.y, 0), split2(y.z, y.w, 0));
+              if (NS == 2) *reinterpret_cast<uint2 *>(r + 64) = make_uint2(split2(y.x, y.y, 1), split2(y.z, y.w, 1));
             }
           }
         }
         if (!waited) WAIT(1, rce_bar(slot), ((q / p.nrc) & 1) ^ 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(rcf_bar(slot));
+        TL(4);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(rece_bar(rb));  // this warp no longer reads s_rec[rb]
     }
   } else if (warp < kMmaWarp0) {
     // ===================== builders: thread r owns tile slot r = TMEM lane r =====================
-    // Unit = (channel block kb, active kernel offset k) of a tile; the CTA's j-th unit lives in stage j % na and is
-    // assembled by builder group j % kBuildGroups: every thread whose slot has a neighbour through offset k copies
-    // that neighbour's converted row (row cache, shared memory) into registers and all 128 threads store their
-    // registers to the unit's TMEM operand slot.  Lanes without a neighbour store stale registers: the MMA never
-    // reads them into a live accumulator lane (disable-output-lane mask).
+    // Unit = (channel block kb, active kernel offset k) of a tile; a STAGE is up to `us` consecutive active offsets of
+    // one (tile, kb) pass, assembled by builder group (stage counter mod groups): every thread whose slot has a
+    // neighbour through the unit's offset copies that neighbour's converted row (row cache, shared memory) into
+    // registers and all 128 threads store their registers to the unit's TMEM operand slot.  Lanes without a neighbour
+    // store stale registers: the MMA never reads them into a live accumulator lane (disable-output-lane mask).
+    // One barrier round trip, one fence and one arrive per stage; the row indices of the group's NEXT stage are fetched
+    // while the current one is assembled.
+    // The builders hold a 32-register operand row plus the next stage's row indices: they take the registers the
+    // issuers and producers give back (setmaxnreg moves them between whole warpgroups).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
     const int bw = warp - kBuildWarp0;
     const uint32_t g = (uint32_t)bw >> 2, w4 = (uint32_t)bw & 3u;
     const uint32_t slot_r = w4 * 32 + (uint32_t)lane;
     const uint32_t s_rc32 = smem_u32(s_rc), s_rec32 = smem_u32(s_rec);
     const uint32_t tlane = colA + ((w4 * 32u) << 16);
     const uint32_t hdr_off = 16u * (uint32_t)p.K;
-    uint32_t it = 0, q = 0, j = 0;  // j = the CTA's unit counter at the start of the current pass
+    uint32_t it = 0, q = 0, Q = 0;  // Q = the CTA's stage counter at the start of the current pass
     uint4 v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = make_uint4(0u, 0u, 0u, 0u);
@@ -654,47 +686,96 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       WAIT(0, recf_bar(rb), (it / p.nrec) & 1);
       const uint32_t rec32 = s_rec32 + rb * rec_buf;
       const uint32_t nact = lds32(rec32 + hdr_off + 12);
-      const uint32_t kl = lds_u8(rec32 + hdr_off + 16 + (uint32_t)lane);  // lane l: the l-th active offset
-      const uint32_t locs32 = rec32 + hdr_off + 48 + slot_r * 2;          // loc[k][slot_r] at + 256 k
+      const bool big = lds32(rec32 + hdr_off) > (uint32_t)kRcap;  // more distinct rows than a row-cache buffer holds
+      const uint32_t locs32 = rec32 + hdr_off + 48 + slot_r * 2;  // loc row of the i-th active offset at + 256 i
+      const uint32_t nq = (nact + us - 1) / us;                    // stages of one pass
       for (int kb = 0; kb < KB; ++kb, ++q) {
         const uint32_t slot = q % p.nrc;
         WAIT(1, rcf_bar(slot), (q / p.nrc) & 1);
+        TL(5);
         const uint32_t rcb = s_rc32 + slot * kRcBuf;
-        // this group's units of the pass: ranks r = g - j (mod groups), step groups.  The row index of the NEXT unit is
-        // fetched while the current one is assembled, so the per-unit chain is rows -> (slot free) -> TMEM store.
-        uint32_t r = (g - j) & (kBuildGroups - 1);
-        uint32_t loc = 0xFFFFu;
-        if (r < nact) loc = lds_u16(locs32 + 256u * __shfl_sync(0xffffffffu, kl, (int)r));
-        for (; r < nact; r += kBuildGroups) {
-          const uint32_t jj = j + r, stage = jj & (na - 1), phase = (jj >> p.lna) & 1;
-          // the next unit's offset: the shuffle is issued now and consumed after the stage wait
-          const uint32_t rn = r + kBuildGroups;
-          const uint32_t kn = __shfl_sync(0xffffffffu, kl, (int)(rn & 31u));
-          uint32_t has = loc < (uint32_t)kRcap && !(p.dbg & 2);
-          if (loc >= (uint32_t)kRcap && loc != 0xFFFFu) {  // overflow rows of a tile with > kRcap distinct rows
-#pragma unroll
-            for (uint32_t c = 0; c < 8; ++c)
-              v[c] = fetch_direct(p.src, p.Cin, p.vec4, p.in_relu, p.uidx + tile * (int64_t)(kTileM * p.K), loc,
-                                  kb * CPU + (NS == 2 ? (int)(c & 3u) : (int)c) * 8, NS == 2 ? (int)(c >> 2) : 0,
-                                  s_scale, s_shift);
+        uint32_t i = (g - Q) & (kBuildGroups - 1);
+        if (!big) {
+          // ---- the hot loop: every row of the tile is in the row cache ----
+          uint32_t loc0 = 0xFFFFu, loc1 = 0xFFFFu, loc2 = 0xFFFFu, loc3 = 0xFFFFu;
+          if (i < nq) {
+            const uint32_t r0 = i * us, la = locs32 + 256u * r0;
+            loc0 = lds_u16(la);
+            if (us > 1 && r0 + 1 < nact) loc1 = lds_u16(la + 256);
+            if (us > 2 && r0 + 2 < nact) loc2 = lds_u16(la + 512);
+            if (us > 3 && r0 + 3 < nact) loc3 = lds_u16(la + 768);
           }
-          // probe the stage's empty barrier, fetch this lane's row from the row cache, then consume the probe
-          const long long tw0 = DIAG ? clock64() : 0;
-          mbar_wait_and_load_row(aempty_bar(stage), phase ^ 1, v, rcb + (loc & (kRcap - 1)) * kRowB, rc_swz(loc) << 4, has);
-          if (DIAG) dg[2] += clock64() - tw0;
-          tc_fence_after();
-          const long long ts0 = DIAG ? clock64() : 0;
-          if (!(p.dbg & 4)) tmem_st_row(tlane + stage * kSlotCols, v);
-          uint32_t loc_n = 0xFFFFu;
-          if (rn < nact) loc_n = lds_u16(locs32 + 256u * kn);
-          tmem_wait_st();
-          tc_fence_before();
-          if (DIAG) dg[3] += clock64() - ts0;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(afull_bar(stage));
-          loc = loc_n;
+          for (; i < nq; i += kBuildGroups) {
+            const uint32_t Qi = Q + i, stage = Qi & (na - 1), phase = (Qi >> p.lna) & 1;
+            const uint32_t t0 = tlane + stage * us * kSlotCols;
+            const uint32_t nu = min(us, nact - i * us);
+            // unit 0: probe the stage's empty barrier, fetch this lane's row under the probe, then consume the probe
+            const long long tw0 = DIAG ? clock64() : 0;
+            mbar_wait_and_load_row(aempty_bar(stage), phase ^ 1, v, rcb + loc0 * kRowStride, loc0 != 0xFFFFu && !(p.dbg & 2));
+            if (DIAG) dg[2] += clock64() - tw0;
+            TL(6);
+            tc_fence_after();
+            const long long ts0 = DIAG ? clock64() : 0;
+            if (!(p.dbg & 4)) tmem_st_row(t0, v);
+            if (nu > 1) {
+              load_row(v, rcb + loc1 * kRowStride, loc1 != 0xFFFFu && !(p.dbg & 2));
+              if (!(p.dbg & 4)) tmem_st_row(t0 + kSlotCols, v);
+            }
+            if (nu > 2) {
+              load_row(v, rcb + loc2 * kRowStride, loc2 != 0xFFFFu && !(p.dbg & 2));
+              if (!(p.dbg & 4)) tmem_st_row(t0 + 2 * kSlotCols, v);
+            }
+            if (nu > 3) {
+              load_row(v, rcb + loc3 * kRowStride, loc3 != 0xFFFFu && !(p.dbg & 2));
+              if (!(p.dbg & 4)) tmem_st_row(t0 + 3 * kSlotCols, v);
+            }
+            if (DIAG) dg[3] += clock64() - ts0;
+            // row indices of this group's next stage (consumed one iteration later)
+            const uint32_t rn = (i + kBuildGroups) * us, la = locs32 + 256u * rn;
+            loc0 = loc1 = loc2 = loc3 = 0xFFFFu;
+            if (rn < nact) loc0 = lds_u16(la);
+            if (us > 1 && rn + 1 < nact) loc1 = lds_u16(la + 256);
+            if (us > 2 && rn + 2 < nact) loc2 = lds_u16(la + 512);
+            if (us > 3 && rn + 3 < nact) loc3 = lds_u16(la + 768);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(afull_bar(stage));
+            TL(7);
+          }
+        } else {
+          // ---- tiles that read more distinct rows than the row cache holds (dense blobs, random maps, the 2x2x2 strided
+          // convolutions): rows beyond the cache are fetched from global memory and converted in place; kept out of the
+          // hot loop ----
+          const int32_t *urows = p.uidx + tile * (int64_t)(kTileM * p.K);
+          for (; i < nq; i += kBuildGroups) {
+            const uint32_t Qi = Q + i, stage = Qi & (na - 1), phase = (Qi >> p.lna) & 1;
+            const uint32_t t0 = tlane + stage * us * kSlotCols;
+            const uint32_t nu = min(us, nact - i * us);
+            WAIT(2, aempty_bar(stage), phase ^ 1);
+            tc_fence_after();
+            for (uint32_t u = 0; u < nu; ++u) {
+              const uint32_t l = lds_u16(locs32 + 256u * (i * us + u));
+              if (l < (uint32_t)kRcap) {  // still in the row cache
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) v[c] = lds128(rcb + l * kRowStride + 16 * c);
+              } else if (l != 0xFFFFu) {
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c)
+                  v[c] = fetch_direct(p.src, p.Cin, p.vec4, p.in_relu, urows, l,
+                                      kb * CPU + (NS == 2 ? (int)(c & 3u) : (int)c) * 8, NS == 2 ? (int)(c >> 2) : 0, s_scale,
+                                      s_shift);
+              }
+              __syncwarp();
+              tmem_st_row(t0 + u * kSlotCols, v);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(afull_bar(stage));
+          }
         }
-        j += nact;
+        Q += nq;
         __syncwarp();
         if (lane == 0) mbar_arrive(rce_bar(slot));  // this warp no longer reads row-cache buffer `slot`
       }
@@ -707,6 +788,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     // own TMEM accumulator.  One thread issues a short MMA every ~39 cycles at best (tools/umma_probe.cu), so
     // N <= 32 needs four issuers and N <= 64 two to keep the tensor pipe at its N/2-cycle floor.
     // The whole warp runs the (warp-uniform) loop; one elected lane issues.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
     const uint32_t mi = uni((uint32_t)(warp - kMmaWarp0));
     if (mi < (uint32_t)p.nmma) {
       const uint32_t nmma = (uint32_t)p.nmma;
@@ -714,7 +796,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       const uint32_t w_base = smem_u32(s_w);
       const uint64_t desc0 = make_desc(0);
       const uint32_t a_base = uni(colA), d_base = uni(tmem_base) + mi * (uint32_t)p.Cout;
-      uint32_t it = 0, j = 0, as = 0, aph = 0;
+      uint32_t it = 0, Q = 0, as = 0, aph = 0;
       const uint32_t hdr_off = 16u * (uint32_t)p.K;
       if (p.resident) mbar_wait(wres_bar, 0);
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -723,55 +805,66 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         const uint32_t rec32 = smem_u32(s_rec) + rb * rec_buf;
         const uint32_t nact = uni(lds32(rec32 + hdr_off + 12));
         const uint32_t kl = lds_u8(rec32 + hdr_off + 16 + (uint32_t)lane);  // lane l: the l-th active offset
+        const uint32_t nq = (nact + us - 1) / us;
         WAIT(1, acce_bar(as), aph ^ 1);
+        TL(8);
         tc_fence_after();
         const uint32_t d = d_base + as * acc_cols;
         for (int kb = 0; kb < KB; ++kb) {
           // 16-channel K steps of this unit that hold real channels
           const int ksteps = min(CPU / 16, (p.Cin - kb * CPU + 15) / 16);
-          for (uint32_t r = (mi - j) & (nmma - 1); r < nact; r += nmma) {
-            const uint32_t k = __shfl_sync(0xffffffffu, kl, (int)r);
-            const uint32_t jj = j + r, stage = jj & (na - 1);
-            // operand rows (tcgen05.st, fenced by the builders) + weights; the unit's valid-slot mask is fetched under
-            // the probe (the MMA takes its complement)
+          // stage Q of the CTA belongs to issuer Q mod nmma, who issues all of its units into its own accumulator
+          for (uint32_t i = (mi - Q) & (nmma - 1); i < nq; i += nmma) {
+            const uint32_t Qi = Q + i, stage = Qi & (na - 1);
+            const uint32_t nu = min(us, nact - i * us);
+            const uint32_t k0 = __shfl_sync(0xffffffffu, kl, (int)((i * us) & 31u));
+            // operand rows (tcgen05.st, fenced by the builders) + weights; the valid-slot mask of the first unit is
+            // fetched under the probe (the MMA takes its complement)
             uint4 vm;
             const long long tw0 = DIAG ? clock64() : 0;
-            mbar_wait_and_load16(afull_bar(stage), (jj >> p.lna) & 1, vm, rec32 + 16 * k);
+            mbar_wait_and_load16(afull_bar(stage), (Qi >> p.lna) & 1, vm, rec32 + 16 * k0);
             if (DIAG) dg[2] += clock64() - tw0;
+            TL(9);
             tc_fence_after();
-            const uint32_t a = a_base + stage * kSlotCols;
-            const uint64_t bd =
-                desc0 + ((w_base + (p.resident ? (uint32_t)(k * KB + kb) : stage) * w_stage) >> 4);
             const long long ti0 = DIAG ? clock64() : 0;
-            if (elect_one()) {
-              const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
-              if ((vm.x | vm.y | vm.z | vm.w) != 0 && !(p.dbg & 1)) {
-                if (NS == 2) {
-                  const uint64_t bm = bd + (b_block >> 4);  // mid block
-                  mma_ts(d, a, bd, idesc, off);
-                  mma_ts(d, a, bm, idesc, off);
-                  mma_ts(d, a + 16, bd, idesc, off);
-                  if (ksteps > 1) {
-                    mma_ts(d, a + 8, bd + 2, idesc, off);
-                    mma_ts(d, a + 8, bm + 2, idesc, off);
-                    mma_ts(d, a + 24, bd + 2, idesc, off);
+            for (uint32_t u = 0; u < nu; ++u) {
+              const uint32_t k = u == 0 ? k0 : __shfl_sync(0xffffffffu, kl, (int)((i * us + u) & 31u));
+              if (elect_one()) {
+                if (u) vm = lds128(rec32 + 16 * k);
+                const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
+                const uint32_t a = a_base + (stage * us + u) * kSlotCols;
+                const uint64_t bd =
+                    desc0 + ((w_base + (p.resident ? (uint32_t)(k * KB + kb) : stage * us + u) * w_stage) >> 4);
+                if ((vm.x | vm.y | vm.z | vm.w) != 0 && !(p.dbg & 1)) {
+                  if (NS == 2) {
+                    const uint64_t bm = bd + (b_block >> 4);  // mid block
+                    mma_ts(d, a, bd, idesc, off);
+                    mma_ts(d, a, bm, idesc, off);
+                    mma_ts(d, a + 16, bd, idesc, off);
+                    if (ksteps > 1) {
+                      mma_ts(d, a + 8, bd + 2, idesc, off);
+                      mma_ts(d, a + 8, bm + 2, idesc, off);
+                      mma_ts(d, a + 24, bd + 2, idesc, off);
+                    }
+                  } else {
+                    mma_ts(d, a, bd, idesc, off);
+                    if (ksteps > 1) mma_ts(d, a + 8, bd + 2, idesc, off);
+                    if (ksteps > 2) mma_ts(d, a + 16, bd + (b_block >> 4), idesc, off);
+                    if (ksteps > 3) mma_ts(d, a + 24, bd + (b_block >> 4) + 2, idesc, off);
                   }
-                } else {
-                  mma_ts(d, a, bd, idesc, off);
-                  if (ksteps > 1) mma_ts(d, a + 8, bd + 2, idesc, off);
-                  if (ksteps > 2) mma_ts(d, a + 16, bd + (b_block >> 4), idesc, off);
-                  if (ksteps > 3) mma_ts(d, a + 24, bd + (b_block >> 4) + 2, idesc, off);
                 }
+                if (u + 1 == nu) mma_commit(aempty_bar(stage));
               }
-              mma_commit(aempty_bar(stage));
+              __syncwarp();
             }
-            __syncwarp();
             if (DIAG) dg[3] += clock64() - ti0;
+            TL(10);
           }
-          j += nact;
+          Q += nq;
         }
         if (elect_one()) mma_commit(accf_bar(as));
         __syncwarp();
+        TL(11);
         if (lane == 0) mbar_arrive(rece_bar(rb));  // this warp no longer reads s_rec[rb]
         if (++as == (uint32_t)p.nbuf) {
           as = 0;
@@ -780,6 +873,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       }
     }
   } else if (warp == kRecWarp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
     // ===================== record producer: bulk copies of each tile's record, p.nrec - 1 tiles ahead ===============
     uint32_t it = 0;
     const uint32_t rec0 = smem_u32(s_rec);
@@ -788,6 +882,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       const int4 m = __ldg(p.meta + tile);
       const uint32_t ub = (min(uni((uint32_t)m.y), (uint32_t)kRcap) * 4u + 15u) & ~15u;
       WAIT_RELAXED(0, rece_bar(rb), ((it / p.nrec) & 1) ^ 1);
+      TL(12);
       if (elect_one()) {
         mbar_expect_tx(recf_bar(rb), rec_main + ub);
         const uint32_t dst = rec0 + rb * rec_buf;
@@ -796,33 +891,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       }
       __syncwarp();
     }
-  } else if (!p.resident) {
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
+    if (!p.resident && warp < kWgtWarp0 + kWgtWarps) {
     // ===================== weight producers: bulk copy of each unit's pre-swizzled weight block into its stage =====
     const uint32_t wi = uni((uint32_t)(warp - kWgtWarp0));
     if (wi < (uint32_t)p.nwp) {
-      uint32_t j = 0;
+      uint32_t Q = 0;
       const uint32_t w_base = smem_u32(s_w);
       const uint32_t nwp = (uint32_t)p.nwp;  // a power of two
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const uint32_t nact = uni((uint32_t)__popc((uint32_t)__ldg(&p.meta[tile].z)));
         const uint32_t kl = __ldg(p.recs + tile * (int64_t)rec_main + 16 * p.K + 16 + lane);  // the record's klist
+        const uint32_t nq = (nact + us - 1) / us;
         for (int kb = 0; kb < KB; ++kb) {
-          for (uint32_t r = (wi - j) & (nwp - 1); r < nact; r += nwp) {
-            const uint32_t k = __shfl_sync(0xffffffffu, kl, (int)r);
-            const uint32_t jj = j + r, sw = jj & (na - 1);
-            WAIT(0, aempty_bar(sw), ((jj >> p.lna) & 1) ^ 1);
+          for (uint32_t i = (wi - Q) & (nwp - 1); i < nq; i += nwp) {
+            const uint32_t Qi = Q + i, sw = Qi & (na - 1);
+            const uint32_t nu = min(us, nact - i * us);
+            uint32_t ku[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) ku[u] = __shfl_sync(0xffffffffu, kl, (int)((i * us + u) & 31u));
+            WAIT(0, aempty_bar(sw), ((Qi >> p.lna) & 1) ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(afull_bar(sw), w_stage);
-              bulk_g2s(w_base + sw * w_stage, p.packed + (size_t)(k * KB + kb) * w_stage, w_stage, afull_bar(sw));
+              mbar_expect_tx(afull_bar(sw), nu * w_stage);
+#pragma unroll
+              for (uint32_t u = 0; u < 4; ++u)
+                if (u < nu)
+                  bulk_g2s(w_base + (sw * us + u) * w_stage, p.packed + (size_t)(ku[u] * KB + kb) * w_stage, w_stage,
+                           afull_bar(sw));
             }
             __syncwarp();
           }
-          j += nact;
+          Q += nq;
         }
       }
     }
+    }
   }
 
+#undef TL
 #undef WAIT
 #undef WAIT_RELAXED
   if (DIAG && p.diag != nullptr && blockIdx.x == 0 && lane == 0) {
@@ -880,33 +987,43 @@ static int plan_launch(wsis::umma::Params &p, int K, int Cin, int Cout, int NS, 
   p.KB = (Cin + cpu - 1) / cpu;
   // one thread issues a short MMA every ~39 cycles: N/2-cycle MMAs need 4 (N <= 32) or 2 (N <= 64) issuers
   p.nmma = Cout <= 32 ? 4 : Cout <= 64 ? 2 : 1;
+  if (const char *e = getenv("WSIS_CONV_NMMA")) p.nmma = std::max(1, std::min(p.nmma, atoi(e)));
   p.nacc = p.nmma;
   // accumulators are double buffered when that leaves at least four operand slots
   p.nbuf = (2 * p.nacc * Cout + 4 * kSlotCols <= 512) ? 2 : 1;
   const int slots = (512 - p.nbuf * p.nacc * Cout) / kSlotCols;
   WSIS_CHECK(slots >= 2, "conv_umma: no TMEM left for operand slots at Cout=%d", Cout);
-  int lna_max = slots >= 8 ? 3 : slots >= 4 ? 2 : 1;
-  if (const char *e = getenv("WSIS_CONV_LNA")) lna_max = std::min(lna_max, atoi(e));
   const int64_t w_stage = 2 * (int64_t)Cout * 64, w_all = (int64_t)K * p.KB * w_stage;
   p.resident = w_all <= kResidentBytes;
   p.nwp = kWgtWarps;
   const int64_t rec_buf = rec_stride_bytes(K) + kRcap * 4;
-  static const int pref[][3] = {{3, 3, 3}, {3, 3, 2}, {3, 2, 2}, {2, 3, 2}, {2, 2, 2}, {2, 1, 2}, {1, 1, 2}};  // {lna, nrc, nrec}
+  // The ring holds at most `slots` operand slots; its throughput is slots / (round trip of a slot: TMEM store, hand-off,
+  // MMA issue + execution, hand-off back), so all of them are used: stages x units per stage = slots (a power of two,
+  // stages a multiple of the issuers and of the builder groups so that every stage has one owner of each kind).
+  // One unit per stage unless WSIS_CONV_US says otherwise: measured best (profiles/README.md).
+  int us_want = 1;
+  if (const char *e = getenv("WSIS_CONV_US")) us_want = std::max(1, std::min(4, atoi(e)));
+  int pool = slots >= 8 ? 8 : slots >= 4 ? 4 : 2;
+  static const int pref[][2] = {{3, 3}, {3, 2}, {2, 2}, {1, 2}, {1, 1}};  // {row-cache buffers, record buffers}
   const int64_t budget = 227 * 1024;
   int64_t smem = 0;
   bool fit = false;
-  for (auto &c : pref) {
-    if (c[0] > lna_max) continue;
-    const int na = 1 << c[0];
-    if (na < p.nmma || na < kBuildGroups) continue;  // every stage belongs to one issuer and one builder group
-    const int64_t misc = 1024 /*align*/ + 2 * p.KB * cpu * 4 + (2 * na + 2 * c[1] + 2 * c[2] + 5) * 8 + 64;
-    smem = misc + (p.resident ? w_all : na * w_stage) + c[1] * (int64_t)kRcBuf + c[2] * rec_buf;
-    if (smem <= budget) {
-      p.lna = c[0];
-      p.nrc = c[1];
-      p.nrec = c[2];
-      fit = true;
-      break;
+  for (; pool >= 2 && !fit; pool >>= 1) {
+    int us_ = std::min(us_want, pool / std::max(p.nmma, kBuildGroups));
+    if (us_ < 1) continue;  // fewer slots than issuers / builder groups
+    if (us_ == 3) us_ = 2;
+    const int na = pool / us_;
+    for (auto &c : pref) {
+      const int64_t misc = 1024 /*align*/ + 2 * p.KB * cpu * 4 + (2 * na + 2 * c[0] + 2 * c[1] + 5) * 8 + 64;
+      smem = misc + (p.resident ? w_all : (int64_t)pool * w_stage) + c[0] * (int64_t)kRcBuf + c[1] * rec_buf;
+      if (smem <= budget) {
+        p.us = us_;
+        p.lna = na == 8 ? 3 : na == 4 ? 2 : na == 2 ? 1 : 0;
+        p.nrc = c[0];
+        p.nrec = c[1];
+        fit = true;
+        break;
+      }
     }
   }
   WSIS_CHECK(fit, "conv_umma: shared memory budget exceeded for Cin=%d Cout=%d K=%d", Cin, Cout, K);
@@ -955,8 +1072,8 @@ int wsis_conv_umma_plan(int K, int Cin, int Cout, int precision, int32_t *plan) 
   Params p;
   int64_t smem = 0;
   if (plan_launch(p, K, Cin, Cout, precision == 3 ? 2 : 1, &smem)) return 1;
-  const int out[10] = {(int)smem, 1 << p.lna, p.nrc, p.nrec, kBuildGroups, p.nacc, p.nmma, p.nbuf, p.resident, p.nwp};
-  for (int i = 0; i < 10; ++i) plan[i] = out[i];
+  const int out[11] = {(int)smem, 1 << p.lna, p.nrc, p.nrec, kBuildGroups, p.nacc, p.nmma, p.nbuf, p.resident, p.nwp, p.us};
+  for (int i = 0; i < 11; ++i) plan[i] = out[i];
   return 0;
 }
 

@@ -45,8 +45,9 @@ __global__ void iota_kernel(int32_t *order, int64_t N, int64_t n_pad) {
 //   record (records + t * rec_stride_bytes(K), all of it meaningful)
 //     [0, 16K)                 valid[K][4]  u32   bit r of valid[k] = tile slot r has a source row through offset k
 //     [16K, 16K + 48)          nU u32 | amask u32 | P u32 | nact u32 | klist u8[32]: the nact active offsets, ascending
-//     [16K + 48, 16K+48+256K)  loc[K][128]  u16   index of slot r's source row through offset k in the tile's list of
-//                                                 DISTINCT source rows (0xFFFF where valid[k] has no bit)
+//     [16K + 48, 16K+48+256K)  loc[K][128]  u16   row i < nact belongs to offset klist[i]: index of slot r's source row
+//                                                 through that offset in the tile's list of DISTINCT source rows
+//                                                 (0xFFFF where the slot has none); rows >= nact are unused
 //   unique rows (uidx + t * 128K)  i32[nU]        the distinct source rows the tile reads; a surface patch of 128
 //                                                 voxels reads ~160-230 distinct rows through ~480-1400 entries, so the
 //                                                 conv kernel fetches (and converts) every source row ONCE per tile
@@ -132,6 +133,9 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
   }
   __syncthreads();
   const int nU = s_pre[4 * K];
+  uint32_t amask = 0;  // offsets with at least one entry (every thread computes it: K <= 32 counters)
+  for (int k = 0; k < K; ++k)
+    if (s_cnt[k] > 0) amask |= 1u << k;
   int32_t *u = uidx + t * (int64_t)(kTile * K);
   uint16_t *loc = reinterpret_cast<uint16_t *>(rec + rec_hdr_bytes(K));
   for (int k = 0; k < K; ++k) {
@@ -143,8 +147,11 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
       l = (uint16_t)rank;
       if (key == k * kTile + r) u[rank] = v;
     }
-    loc[k * kTile + r] = l;
+    // loc rows are stored compacted over the ACTIVE offsets (row = rank of k in amask): the conv builders walk them
+    // by rank without a lookup; a tile without any entry keeps one all-0xFFFF row (its dummy unit)
+    if ((amask >> k) & 1u) loc[__popc(amask & ((1u << k) - 1u)) * kTile + r] = l;
   }
+  if (amask == 0) loc[r] = 0xFFFFu;
   if (r == 0) {
     uint32_t am = 0;
     int P = 0;

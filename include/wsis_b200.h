@@ -150,9 +150,9 @@ int wsis_conv_umma_supported(int Cin, int Cout);
 int64_t wsis_conv_pack_bytes(int K, int Cin, int Cout, int precision);
 int wsis_conv_pack_weights(const float *W, int K, int Cin, int Cout, int transpose_w, int precision, void *packed,
                            wsis_stream_t stream);
-/* Launch plan of a layer shape (pure host arithmetic, no device needed): plan = int32[10] {dynamic shared-memory
+/* Launch plan of a layer shape (pure host arithmetic, no device needed): plan = int32[11] {dynamic shared-memory
  * bytes, pipeline stages, row-cache buffers, record buffers, builder groups, TMEM accumulators, MMA issuers,
- * accumulator buffers (1|2), weights resident in shared memory (0|1), weight-producer warps}.
+ * accumulator buffers (1|2), weights resident in shared memory (0|1), weight-producer warps, units per stage}.
  * Fails when no pipeline fits the 227 KB of shared memory / 512 TMEM columns. */
 int wsis_conv_umma_plan(int K, int Cin, int Cout, int precision, int32_t *plan);
 int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, const int32_t *meta,

@@ -510,7 +510,7 @@ def test_clustering_fragments_and_edge_cases():
 def test_conv_umma_launch_plan_exists_for_every_layer_shape():
     """Host-only: every (Cin, Cout, K, precision) the tensor-core conv accepts has a pipeline that fits the 227 KB of
     shared memory and the 512 TMEM columns, and the invariants the kernel's barrier protocol relies on hold (stages are
-    a power of two, every stage has one issuer and one builder group: groups | stages, nmma | stages)."""
+    a power of two and a multiple of the builder groups and of the issuers: every stage has one owner of each kind)."""
     from wsis_b200._lib import lib
     L = lib()
     shapes = [(6, 32), (32, 32), (64, 32), (32, 64), (64, 64), (128, 64), (96, 96), (192, 96), (128, 128), (256, 128),
@@ -518,19 +518,19 @@ def test_conv_umma_launch_plan_exists_for_every_layer_shape():
     for cin, cout in shapes:
         for K in (1, 8, 27, 32):
             for prec in (1, 3):
-                plan = (ctypes.c_int32 * 10)()
+                plan = (ctypes.c_int32 * 11)()
                 L.call("wsis_conv_umma_plan", K, cin, cout, prec, plan)
-                smem, na, nrc, nrec, nbg, nacc, nmma, nbuf, resident, nwp = list(plan)
+                smem, na, nrc, nrec, nbg, nacc, nmma, nbuf, resident, nwp, us = list(plan)
                 assert 0 < smem <= 227 * 1024, (cin, cout, K, prec, smem)
-                assert na in (2, 4, 8) and nrc >= 1 and nrec >= 2 and nbuf in (1, 2) and nwp >= 1
-                assert na % nbg == 0 and na % nmma == 0 and nacc == nmma
-                assert nbuf * nacc * cout + 32 * na <= 512            # accumulators + operand slots fit TMEM
+                assert na in (2, 4, 8) and nrc >= 1 and nrec >= 2 and nbuf in (1, 2) and nwp in (1, 2) and 1 <= us <= 4
+                assert na % nbg == 0 and na % nmma == 0 and nacc == nmma and nmma in (1, 2, 4)
+                assert nbuf * nacc * cout + 32 * na * us <= 512       # accumulators + operand slots fit TMEM
     # the level-1 layers keep their whole packed weight in shared memory and run four issuers
-    plan = (ctypes.c_int32 * 10)()
+    plan = (ctypes.c_int32 * 11)()
     L.call("wsis_conv_umma_plan", 27, 32, 32, 3, plan)
-    assert plan[1] == 8 and plan[6] == 4 and plan[8] == 1
+    assert plan[1] == 8 and plan[6] == 4 and plan[8] == 1 and plan[10] == 1
     L.call("wsis_conv_umma_plan", 27, 64, 64, 3, plan)
-    assert plan[1] == 8 and plan[6] == 2 and plan[7] == 2 and plan[8] == 0
+    assert plan[1] == 8 and plan[6] == 2 and plan[7] == 2 and plan[8] == 0 and plan[10] == 1
     with pytest.raises(RuntimeError):
         L.call("wsis_conv_umma_plan", 27, 32, 24, 3, plan)      # Cout not a multiple of 16
 
@@ -562,8 +562,8 @@ def test_conv_umma_barrier_protocol_model():
     """tools/protocol_model.py transcribes the control flow of every role of conv_umma_kernel (ring indices, parities,
     arrival counts) and checks under random schedules that no parity wait passes before its logical generation has
     completed, that every consumer finds the buffer contents it expects, and that nothing deadlocks -- for every
-    launch plan the host planner can produce.  A ring with fewer stages than builder groups / issuers (a stage shared
-    by two owners) must be caught."""
+    launch plan the host planner can produce.  A ring with fewer stages than issuers (an issuer whose next stage is two
+    generations ahead on the same buffer) must be caught."""
     import random
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import protocol_model as pm
@@ -573,20 +573,20 @@ def test_conv_umma_barrier_protocol_model():
     for cin, cout in [(6, 32), (32, 32), (64, 64), (96, 96), (128, 128), (160, 160), (320, 160), (1024, 256), (32, 16)]:
         for K in (8, 27, 32):
             for prec in (1, 3):
-                plan = (ctypes.c_int32 * 10)()
+                plan = (ctypes.c_int32 * 11)()
                 L.call("wsis_conv_umma_plan", K, cin, cout, prec, plan)
-                _, na, nrc, nrec, nbg, _, nmma, nbuf, resident, nwp = list(plan)
-                plans.add((na, nrc, nrec, nbg, nmma, nbuf, resident, nwp))
+                _, na, nrc, nrec, nbg, _, nmma, nbuf, resident, nwp, us = list(plan)
+                plans.add((na, nrc, nrec, nbg, nmma, nbuf, resident, nwp, us))
     assert len(plans) >= 3
     rng = random.Random(5)
-    for na, nrc, nrec, nbg, nmma, nbuf, resident, nwp in sorted(plans):
-        kw = dict(nbuf=nbuf, resident=bool(resident), nwp=nwp)
+    for na, nrc, nrec, nbg, nmma, nbuf, resident, nwp, us in sorted(plans):
+        kw = dict(nbuf=nbuf, resident=bool(resident), nwp=nwp, us=us)
         for seed in range(10):
             tiles = pm.random_tiles(rng, rng.randint(1, 7))
             assert pm.Cta(tiles, na, nrc, nrec, nbg, nmma, **kw).run(seed)
         assert pm.Cta([(1, 1)], na, nrc, nrec, nbg, nmma, **kw).run(0)              # a single one-unit tile
         assert pm.Cta([(27, 5)] * 3, na, nrc, nrec, nbg, nmma, **kw).run(1)         # the widest layer
-    with pytest.raises(pm.ProtocolError):                                    # four issuers alternate on two stages
+    with pytest.raises(pm.ProtocolError):                                    # four issuers on two stages
         for seed in range(50):
             pm.Cta(pm.random_tiles(rng, 6), 2, 2, 2, 2, 4).run(seed)
 

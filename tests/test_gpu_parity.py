@@ -544,7 +544,10 @@ def _decode_records(t, K):
         nU, amask, P, nact = int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[3])
         klist = r[16 * K + 16:16 * K + 48]
         assert [int(k) for k in klist[:nact]] == [k for k in range(K) if amask >> k & 1] and nact == bin(amask).count("1")
-        loc = r[16 * K + 48:].view(np.uint16).reshape(K, 128).astype(np.int64)
+        locr = r[16 * K + 48:].view(np.uint16).reshape(K, 128).astype(np.int64)   # rows in klist (rank) order
+        loc = np.full((K, 128), 0xFFFF, np.int64)
+        for i in range(nact):
+            loc[int(klist[i])] = locr[i]
         bits = np.unpackbits(valid.view(np.uint8).reshape(K, 16), axis=1, bitorder="little").astype(bool)
         assert P == bits.sum() and amask == (sum(1 << k for k in range(K) if bits[k].any()) or 1)
         assert list(meta[ti]) == [t.stride, nU, amask, P]

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--shape", default="64x64")
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--level", type=int, default=1)
+    ap.add_argument("--timeline", type=int, nargs=2, default=None, help="print CTA 0's events between two cycle counts")
     args = ap.parse_args()
     from wsis_b200 import ops as W
     from wsis_b200 import synthetic
@@ -50,12 +51,13 @@ def main():
     w = (torch.rand((27, cin, cout), device=dev, generator=g) - 0.5) / cin ** 0.5
     packed = W.PackedWeights()
     W.sparse_conv(x, w, rb.nbr_in, N, 1, packed=packed, precision=args.precision, tiles=tiles)
-    buf = torch.zeros(23 * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(256 + 24 * 512, dtype=torch.int64, device=dev)
     lib().call("wsis_conv_debug_stats", ctypes.c_void_p(buf.data_ptr()))
     W.sparse_conv(x, w, rb.nbr_in, N, 1, packed=packed, precision=args.precision, tiles=tiles)
     torch.cuda.synchronize()
     lib().call("wsis_conv_debug_stats", None)
-    st = buf.cpu().numpy().reshape(23, 8)
+    raw = buf.cpu().numpy()
+    st = raw[:23 * 8].reshape(23, 8)
     tiles_cta0 = -(-tiles.num_tiles // 148)
     meta = tiles.meta.cpu().numpy()
     units = int(sum(bin(int(m) & 0xffffffff).count("1") for m in meta[0::148, 2])) * (-(-cin // (32 if args.precision == "fp32" else 64)))
@@ -68,6 +70,21 @@ def main():
         out["roles"].append({"warp": wi, "role": name, "cycles": tot, "cyc_per_unit": round(tot / max(units, 1), 1),
                              "waits": {k: round(int(st[wi, 1 + i]) / tot, 3) for i, k in enumerate(waits)}})
     print(json.dumps(out, indent=None))
+    if args.timeline:
+        names = {1: "epi: acc full", 2: "epi: acc released", 3: "gather: record ready", 4: "gather: pass done",
+                 5: "build: row cache ready", 6: "build: slots free (probe passed)", 7: "build: stage full",
+                 8: "issue: acc free", 9: "issue: stage full seen", 10: "issue: stage committed", 11: "issue: tile committed",
+                 12: "records: buffer free"}
+        ev = []
+        for w in range(24):
+            for x in raw[256 + w * 512:256 + (w + 1) * 512]:
+                if x:
+                    ev.append((int(x) >> 8, w, int(x) & 0xff))
+        ev.sort()
+        lo, hi = args.timeline
+        for t, w, c in ev:
+            if lo <= t <= hi:
+                print("%9d  warp %2d %-9s %s" % (t, w, ROLES[w][0] if w < len(ROLES) else "?", names.get(c, c)), file=sys.stderr)
     for r in out["roles"]:
         print("%2d %-9s %9d cyc  %7.1f/unit  %s" % (r["warp"], r["role"], r["cycles"], r["cyc_per_unit"], r["waits"]), file=sys.stderr)
 

@@ -44,16 +44,17 @@ def wait(bar, parity, needed_phases, what):
 
 
 class Cta(object):
-    """One persistent CTA working through `tiles` = list of (number of active offsets, KB)."""
+    """One persistent CTA working through `tiles` = list of (number of active offsets, KB).  A pipeline STAGE holds up
+    to `us` consecutive active offsets of one (tile, channel block) pass."""
 
-    def __init__(self, tiles, na, nrc, nrec, nbg, nmma, nbuf=2, resident=False, nwp=2, gather_warps=4, epi_warps=4):
+    def __init__(self, tiles, na, nrc, nrec, nbg, nmma, nbuf=2, resident=False, nwp=2, us=4, gather_warps=4, epi_warps=4):
         assert na & (na - 1) == 0
         self.tiles, self.na, self.nrc, self.nrec, self.nbg, self.nmma = tiles, na, nrc, nrec, nbg, nmma
-        self.nbuf, self.resident, self.nwp = nbuf, resident, nwp
+        self.nbuf, self.resident, self.nwp, self.us = nbuf, resident, nwp, us
         self.G, self.E = gather_warps, epi_warps
         self.lna = na.bit_length() - 1
         self.afull = [Barrier(4 + (0 if resident else 1)) for _ in range(na)]  # 4 builder warps (+ weight expect_tx)
-        self.aempty = [Barrier(1) for _ in range(na)]                      # tcgen05.commit
+        self.aempty = [Barrier(1) for _ in range(na)]                      # the owning issuer's tcgen05.commit
         self.rcf = [Barrier(gather_warps) for _ in range(nrc)]
         self.rce = [Barrier(4 * nbg) for _ in range(nrc)]
         self.recf = [Barrier(1) for _ in range(nrec)]
@@ -61,12 +62,15 @@ class Cta(object):
         self.accf = [Barrier(nmma) for _ in range(2)]
         self.acce = [Barrier(epi_warps) for _ in range(2)]
         # buffer contents (what the consumer must find)
-        self.stage_rows = [[None] * 4 for _ in range(na)]                  # unit id written by each builder warp
-        self.stage_w = [None] * na                                         # unit id of the weight block
+        self.stage_rows = [[None] * 4 for _ in range(na)]                  # stage id written by each builder warp
+        self.stage_w = [None] * na                                         # stage id of the weight blocks
         self.rc = [None] * nrc                                             # pass id
         self.rec = [None] * nrec                                           # tile iteration
         self.acc_tile = [None, None]                                       # tile whose MMAs went into the buffer
-        self.done_units, self.done_tiles = [], []
+        self.done_stages, self.done_tiles = [], []
+
+    def _nq(self, nact):
+        return -(-nact // self.us)
 
     # ---- roles (each a generator; `yield` = be descheduled) ----
     def record_producer(self):
@@ -80,16 +84,16 @@ class Cta(object):
     def weight_producer(self, wi):
         if self.resident:
             return
-        j = 0
+        Q = 0
         for nact, KB in self.tiles:
-            for _ in range(KB * nact):
-                if j % self.nwp == wi:
-                    s = j & (self.na - 1)
-                    yield from wait(self.aempty[s], ((j >> self.lna) & 1) ^ 1, j >> self.lna, "weight slot free")
-                    self.stage_w[s] = j
+            for _ in range(KB * self._nq(nact)):
+                if Q % self.nwp == wi:
+                    s = Q & (self.na - 1)
+                    yield from wait(self.aempty[s], ((Q >> self.lna) & 1) ^ 1, Q >> self.lna, "weight slot free")
+                    self.stage_w[s] = Q
                     yield
                     self.afull[s].arrive()
-                j += 1
+                Q += 1
 
     def gatherer(self, g):
         q = 0
@@ -111,7 +115,7 @@ class Cta(object):
 
     def builder(self, bw):
         g, w4 = bw // 4, bw % 4
-        q = j = 0
+        q = Q = 0
         for it, (nact, KB) in enumerate(self.tiles):
             rb = it % self.nrec
             yield from wait(self.recf[rb], (it // self.nrec) & 1, it // self.nrec + 1, "record ready (builder)")
@@ -120,23 +124,23 @@ class Cta(object):
             for kb in range(KB):
                 slot = q % self.nrc
                 yield from wait(self.rcf[slot], (q // self.nrc) & 1, q // self.nrc + 1, "row cache full")
-                for _ in range(nact):
-                    if j % self.nbg == g:
-                        stage, phase = j & (self.na - 1), (j >> self.lna) & 1
+                for _ in range(self._nq(nact)):
+                    if Q % self.nbg == g:
+                        stage, phase = Q & (self.na - 1), (Q >> self.lna) & 1
                         if self.rc[slot] != q:
                             raise ProtocolError("builder reads row cache of pass %s, wants %d" % (self.rc[slot], q))
                         yield                                               # rows -> registers
-                        yield from wait(self.aempty[stage], phase ^ 1, j >> self.lna, "operand slot free")
-                        self.stage_rows[stage][w4] = j
+                        yield from wait(self.aempty[stage], phase ^ 1, Q >> self.lna, "operand slots free")
+                        self.stage_rows[stage][w4] = Q
                         yield
                         self.afull[stage].arrive()
-                    j += 1
+                    Q += 1
                 self.rce[slot].arrive()
                 q += 1
             self.rece[rb].arrive()
 
     def issuer(self, mi):
-        j = 0
+        Q = 0
         acc, aph = 0, 0
         for it, (nact, KB) in enumerate(self.tiles):
             rb = it % self.nrec
@@ -144,20 +148,20 @@ class Cta(object):
             if self.rec[rb] != it:
                 raise ProtocolError("issuer reads record of tile %s, wants %d" % (self.rec[rb], it))
             yield from wait(self.acce[acc], aph ^ 1, it // self.nbuf, "accumulator free")
-            for _ in range(nact * KB):
-                if j & (self.nmma - 1) == mi:
-                    sa = j & (self.na - 1)
-                    yield from wait(self.afull[sa], (j >> self.lna) & 1, (j >> self.lna) + 1, "stage full")
-                    if (not self.resident and self.stage_w[sa] != j) or any(r != j for r in self.stage_rows[sa]):
-                        raise ProtocolError("issuer %d, unit %d: stage holds rows %s weights %s"
-                                            % (mi, j, self.stage_rows[sa], self.stage_w[sa]))
+            for _ in range(self._nq(nact) * KB):
+                if Q & (self.nmma - 1) == mi:                              # stage Q belongs to issuer Q mod nmma
+                    sa = Q & (self.na - 1)
+                    yield from wait(self.afull[sa], (Q >> self.lna) & 1, (Q >> self.lna) + 1, "stage full")
+                    if (not self.resident and self.stage_w[sa] != Q) or any(r != Q for r in self.stage_rows[sa]):
+                        raise ProtocolError("issuer %d, stage %d: holds rows %s weights %s"
+                                            % (mi, Q, self.stage_rows[sa], self.stage_w[sa]))
                     if self.acc_tile[acc] not in (None, it):
                         raise ProtocolError("accumulator %d still holds tile %s" % (acc, self.acc_tile[acc]))
                     self.acc_tile[acc] = it
                     yield                                                   # MMAs execute
-                    self.done_units.append(j)
+                    self.done_stages.append(Q)
                     self.aempty[sa].arrive()                                # tcgen05.commit
-                j += 1
+                Q += 1
             yield
             self.accf[acc].arrive()
             self.rece[rb].arrive()
@@ -169,7 +173,7 @@ class Cta(object):
         acc, aph = 0, 0
         for it in range(len(self.tiles)):
             yield from wait(self.accf[acc], aph, it // self.nbuf + 1, "accumulator full")
-            if self.acc_tile[acc] not in (it, None):                        # None: a tile whose units all went elsewhere
+            if self.acc_tile[acc] not in (it, None):                        # None: no issuer had a stage in this tile yet
                 raise ProtocolError("epilogue reads tile %s, wants %d" % (self.acc_tile[acc], it))
             yield
             if w == 0:
@@ -206,14 +210,14 @@ class Cta(object):
                 raise ProtocolError("deadlock: no role makes progress")
         else:
             raise ProtocolError("step budget exhausted")
-        total = sum(n * k for n, k in self.tiles)
-        if sorted(self.done_units) != list(range(total)) or self.done_tiles != list(range(len(self.tiles))):
-            raise ProtocolError("work lost: %d of %d units, tiles %s" % (len(self.done_units), total, self.done_tiles))
+        total = sum(self._nq(n) * k for n, k in self.tiles)
+        if sorted(self.done_stages) != list(range(total)) or self.done_tiles != list(range(len(self.tiles))):
+            raise ProtocolError("work lost: %d of %d stages, tiles %s" % (len(self.done_stages), total, self.done_tiles))
         return True
 
     def _state(self):
         bars = self.afull + self.aempty + self.rcf + self.rce + self.recf + self.rece + self.accf + self.acce
-        return tuple((b.phase, b.pending) for b in bars) + (len(self.done_units),)
+        return tuple((b.phase, b.pending) for b in bars) + (len(self.done_stages),)
 
 
 def random_tiles(rng, n_tiles, max_units=27, max_kb=3):
@@ -222,14 +226,14 @@ def random_tiles(rng, n_tiles, max_units=27, max_kb=3):
 
 if __name__ == "__main__":
     r = random.Random(1)
-    for na, nrc, nbg, nmma, nbuf, res in ((8, 3, 2, 4, 2, True), (8, 3, 2, 2, 2, False), (4, 2, 2, 1, 2, False),
-                                          (8, 2, 2, 1, 1, False), (2, 1, 2, 1, 2, False), (4, 2, 2, 4, 2, False)):
+    for na, nrc, nbg, nmma, nbuf, res, us in ((8, 3, 2, 4, 2, True, 1), (8, 3, 2, 2, 2, False, 1), (4, 2, 2, 1, 2, False, 1),
+                                              (8, 2, 2, 1, 1, False, 1), (4, 1, 2, 4, 2, False, 2), (2, 2, 2, 2, 2, False, 4)):
         for seed in range(20):
-            Cta(random_tiles(r, 6), na, nrc, 2, nbg, nmma, nbuf=nbuf, resident=res).run(seed)
+            Cta(random_tiles(r, 6), na, nrc, 2, nbg, nmma, nbuf=nbuf, resident=res, us=us).run(seed)
     print("protocol ok")
-    try:  # four issuers on a two-stage ring: an issuer's next unit is two generations ahead on the same stage
+    try:  # four issuers on a two-stage ring: an issuer's next stage is two generations ahead on the same buffer
         for seed in range(50):
             Cta(random_tiles(r, 6), 2, 2, 2, 2, 4).run(seed)
-        print("(the nmma > na configuration was not caught)")
+        print("(the issuers > stages configuration was not caught)")
     except ProtocolError as e:
-        print("nmma > na is caught:", e)
+        print("issuers > stages is caught:", e)

@@ -289,6 +289,64 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Cfg c, long long *cycles,
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
 }
 
+// ---- hand-off latency: two warps bounce a token through two mbarriers; mode 0: both sides arrive with mbarrier.arrive,
+// mode 1: the second warp answers with tcgen05.commit (no MMA outstanding), mode 2: commit after one short MMA
+__global__ void __launch_bounds__(256, 1) pingpong_kernel(int mode, int rounds, long long *cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t *sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t *sB = sm + 16384;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 16384 + 16384);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < 4096; e += blockDim.x) reinterpret_cast<uint32_t *>(sB)[e] = 0;
+  if (tid == 0) {
+    mbar_init(smem_u32(bars + 0), 1);
+    mbar_init(smem_u32(bars + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = *s_tmem;
+  const uint32_t b0 = smem_u32(bars + 0), b1 = smem_u32(bars + 1);
+  if (warp == 0) {
+    __syncwarp();
+    const long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b0) : "memory");
+      mbar_wait(b1, r & 1);
+    }
+    const long long t1 = clock64();
+    if (lane == 0) cycles[blockIdx.x] = t1 - t0;
+  } else if (warp == 4) {
+    const uint32_t idesc = make_idesc(32);
+    const uint64_t bd = make_desc(smem_u32(sB));
+    for (int r = 0; r < rounds; ++r) {
+      mbar_wait(b0, r & 1);
+      if (mode == 0) {
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b1) : "memory");
+      } else {
+        if (elect_one()) {
+          if (mode == 2) mma_ts_nomask(tb, tb + 448, bd, idesc);
+          mma_commit(b1);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
 static double median(std::vector<long long> v) {
   std::sort(v.begin(), v.end());
   return (double)v[v.size() / 2];
@@ -304,6 +362,7 @@ int main() {
   CK(cudaMalloc(&d_out, sizeof(float) * 128 * 256));
   const int smem = 8192 * 2 + 256 * 64 * 2 + 256 + 1024;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(pingpong_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   std::vector<long long> h(grid * 3);
   std::vector<float> hout(128 * 256);
 
@@ -363,6 +422,18 @@ int main() {
     std::vector<long long> st(h.begin() + grid, h.begin() + 2 * grid);
     printf("{\"tmem_store\": \"2 x tcgen05.st.32x32b.x16 + wait::st, 4 warps\", \"cyc_per_unit\": %.1f}\n",
            median(st) / units);
+  }
+  // ---- hand-off round trips ----
+  for (int mode = 0; mode < 3; ++mode) {
+    const int rounds = 2000;
+    pingpong_kernel<<<grid, 256, smem>>>(mode, rounds, d_cyc);
+    pingpong_kernel<<<grid, 256, smem>>>(mode, rounds, d_cyc);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), d_cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
+    std::vector<long long> rt(h.begin(), h.begin() + grid);
+    printf("{\"pingpong\": \"%s\", \"cyc_per_round_trip\": %.1f}\n",
+           mode == 0 ? "arrive <-> arrive" : mode == 1 ? "arrive <-> tcgen05.commit (idle pipe)" : "arrive <-> one N=32 MMA + commit",
+           median(rt) / rounds);
   }
   return 0;
 }
