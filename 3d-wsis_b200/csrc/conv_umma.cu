@@ -64,6 +64,8 @@ constexpr int kRowB = 128;    // bytes of one converted row: 32 ch x (hi, mid) o
 constexpr int kRowStride = 144;  // row-cache row pitch: 128 + 16 bytes of padding (see rc layout below)
 constexpr int kRcBuf = kRcap * kRowStride;
 constexpr int kSlotCols = 32;  // TMEM columns of one operand slot (128 B per lane)
+constexpr int kUlSlots = 4;                 // ring of unique-row lists (what the gatherers read), prefetched this deep
+constexpr int kUlBytes = 16 + kRcap * 4;    // {nU, pad} + the first kRcap unique rows of a tile
 constexpr int kResidentBytes = 112 * 1024;  // packed weights up to this size stay in shared memory for the whole launch
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,7 +158,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // branch that consumes it, so the probe's latency and the loads' latency overlap.
 //   rows: v[0..7] <- 8 x 16 bytes at rbase + ((c ^ f) << 4) when `has` (other lanes keep their registers)
 __device__ __forceinline__ void mbar_wait_and_load_row(uint32_t bar, uint32_t parity, uint4 (&v)[8], uint32_t rbase,
-                                                       uint32_t has) {
+                                                       uint32_t has, uint32_t ns) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -175,8 +177,7 @@ __device__ __forceinline__ void mbar_wait_and_load_row(uint32_t bar, uint32_t pa
       "mov.u32 n, 0;\n"
       "@p bra LAB_DONE;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%33], %34;\n"
-      "@p bra LAB_DONE;\n"
+      "nanosleep.u32 %37;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%33], %34;\n"
       "@p bra LAB_DONE;\n"
       "add.u32 n, n, 1;\n"
@@ -190,7 +191,7 @@ __device__ __forceinline__ void mbar_wait_and_load_row(uint32_t bar, uint32_t pa
         "+r"(v[3].w), "+r"(v[4].x), "+r"(v[4].y), "+r"(v[4].z), "+r"(v[4].w), "+r"(v[5].x), "+r"(v[5].y), "+r"(v[5].z),
         "+r"(v[5].w), "+r"(v[6].x), "+r"(v[6].y), "+r"(v[6].z), "+r"(v[6].w), "+r"(v[7].x), "+r"(v[7].y), "+r"(v[7].z),
         "+r"(v[7].w)
-      : "r"(bar), "r"(parity), "r"(rbase), "r"(has)
+      : "r"(bar), "r"(parity), "r"(rbase), "r"(has), "r"(ns)
       : "memory");
   if (!ok) mbar_deadlock(bar, parity);
 }
@@ -216,7 +217,7 @@ __device__ __forceinline__ void load_row(uint4 (&v)[8], uint32_t rbase, uint32_t
       : "memory");
 }
 //   mask: m <- 16 bytes at maddr (the issuer's disable-output-lane mask of the unit)
-__device__ __forceinline__ void mbar_wait_and_load16(uint32_t bar, uint32_t parity, uint4 &m, uint32_t maddr) {
+__device__ __forceinline__ void mbar_wait_and_load16(uint32_t bar, uint32_t parity, uint4 &m, uint32_t maddr, uint32_t ns) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -227,8 +228,7 @@ __device__ __forceinline__ void mbar_wait_and_load16(uint32_t bar, uint32_t pari
       "mov.u32 n, 0;\n"
       "@p bra LAB_DONE;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%5], %6;\n"
-      "@p bra LAB_DONE;\n"
+      "nanosleep.u32 %8;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%5], %6;\n"
       "@p bra LAB_DONE;\n"
       "add.u32 n, n, 1;\n"
@@ -238,7 +238,7 @@ __device__ __forceinline__ void mbar_wait_and_load16(uint32_t bar, uint32_t pari
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok), "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
-      : "r"(bar), "r"(parity), "r"(maddr)
+      : "r"(bar), "r"(parity), "r"(maddr), "r"(ns)
       : "memory");
   if (!ok) mbar_deadlock(bar, parity);
 }
@@ -433,7 +433,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 }
 
 // NS = 2: fp32 contract (hi + mid, 32 channels per unit); NS = 1: bf16 operands (64 channels per unit)
-template <int NS, bool DIAG>
+template <int NS, int US, bool DIAG>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -445,13 +445,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t b_block = (uint32_t)p.Cout * 64u;  // one [Cout x 32 ch] K-major swizzled weight block
   const uint32_t w_stage = 2 * b_block;             // (hi, mid) of 32 channels, or two 32-channel halves of bf16
   const uint32_t rec_main = (uint32_t)rec_stride_bytes(p.K);
-  const uint32_t rec_buf = rec_main + kRcap * 4;  // record + the first kRcap unique rows
-  const uint32_t us = (uint32_t)p.us;  // units per stage
+  const uint32_t rec_buf = rec_main;
+  constexpr uint32_t us = US;  // units per stage
+  const int dbg = DIAG ? p.dbg : 0;  // timing experiments exist in the diagnostics build only
   const uint32_t w_bytes = p.resident ? (uint32_t)(p.K * KB) * w_stage : na * us * w_stage;
   uint8_t *s_w = sm;                                   // weight blocks: ring of na stages, or the whole packed weight
   uint8_t *s_rc = s_w + w_bytes;                       // [nrc][kRcap][128 B]   converted source rows
   uint8_t *s_rec = s_rc + (size_t)p.nrc * kRcBuf;      // [nrec][rec_buf]       tile records (bulk copies)
-  float *s_scale = reinterpret_cast<float *>(s_rec + (size_t)p.nrec * rec_buf);
+  uint8_t *s_ul = s_rec + (size_t)p.nrec * rec_buf;    // [kUlSlots][kUlBytes]  unique-row lists (bulk copies)
+  float *s_scale = reinterpret_cast<float *>(s_ul + kUlSlots * kUlBytes);
   float *s_shift = s_scale + KB * CPU;
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + KB * CPU);
   const uint32_t bar0 = smem_u32(bars);
@@ -466,7 +468,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   auto accf_bar = [&](uint32_t s) { return bar2 + 8u * (2 * p.nrec + s); };
   auto acce_bar = [&](uint32_t s) { return bar2 + 8u * (2 * p.nrec + 2 + s); };
   const uint32_t wres_bar = bar2 + 8u * (2 * p.nrec + 4);
-  const uint32_t nbars = 2 * na + 2 * p.nrc + 2 * p.nrec + 5;
+  auto ulf_bar = [&](uint32_t s) { return wres_bar + 8u * (1 + s); };
+  auto ule_bar = [&](uint32_t s) { return wres_bar + 8u * (1 + kUlSlots + s); };
+  const uint32_t nbars = 2 * na + 2 * p.nrc + 2 * p.nrec + 5 + 2 * kUlSlots;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + nbars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -498,7 +502,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     }
     for (int s = 0; s < p.nrec; ++s) {
       mbar_init(recf_bar(s), 1);
-      mbar_init(rece_bar(s), kGatherWarps + kBuildWarps + p.nmma);
+      mbar_init(rece_bar(s), kBuildWarps + p.nmma);
+    }
+    for (int s = 0; s < kUlSlots; ++s) {
+      mbar_init(ulf_bar(s), 1);
+      mbar_init(ule_bar(s), kGatherWarps);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(accf_bar(s), p.nmma);
@@ -559,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       TL(1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * acc_cols;
-      for (int c0 = 0; c0 < p.Cout && !(p.dbg & 16); c0 += 16) {
+      for (int c0 = 0; c0 < p.Cout && !(dbg & 16); c0 += 16) {
         float4 rn[4];
         const bool more = c0 + 16 < p.Cout;
 #pragma unroll
@@ -607,13 +615,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     const int rsub = gt / LPR, chunk = gt % LPR;
     uint32_t it = 0, q = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t rb = it % p.nrec;
-      WAIT_RELAXED(0, recf_bar(rb), (it / p.nrec) & 1);
+      // the tile's list of distinct rows comes through its own small ring, several tiles ahead of the (large) record
+      // the builders and issuers hold: the gather of tile t+1 does not wait for the record ring to turn over
+      const uint32_t ub = it % kUlSlots;
+      WAIT_RELAXED(0, ulf_bar(ub), (it / kUlSlots) & 1);
       TL(3);
-      const uint8_t *rec = s_rec + (size_t)rb * rec_buf;
+      const uint8_t *ul = s_ul + (size_t)ub * kUlBytes;
       // distinct rows of the tile (the overflow beyond a row-cache buffer is fetched directly by the builders)
-      const int ng = min((int)*reinterpret_cast<const uint32_t *>(rec + 16 * p.K), kRcap);
-      const int32_t *uidx = reinterpret_cast<const int32_t *>(rec + rec_main);
+      const int ng = min((int)*reinterpret_cast<const uint32_t *>(ul), kRcap);
+      const int32_t *uidx = reinterpret_cast<const int32_t *>(ul + 16);
       for (int kb = 0; kb < KB; ++kb, ++q) {
         const uint32_t slot = q % p.nrc;
         const int c0 = kb * CPU + chunk * 4;
@@ -623,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         bool waited = false;
         constexpr int kSweep = kGatherWarps * 32 / LPR;  // rows per load instruction of the gather warps
         constexpr int kInFlight = 8;                     // 16-byte loads in flight per gather lane
-        for (int u0 = 0; u0 < ng; u0 += kInFlight * kSweep) {
+        for (int u0 = 0; u0 < ng && !(dbg & 32); u0 += kInFlight * kSweep) {
           int32_t idx[kInFlight];
           float4 v[kInFlight];
 #pragma unroll
@@ -634,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
 #pragma unroll
           for (int i = 0; i < kInFlight; ++i) {
             const int u = u0 + i * kSweep + rsub;
-            if (u < ng && !(p.dbg & 8)) v[i] = load_row4(p.src, p.Cin, p.vec4, idx[i], c0);
+            if (u < ng && !(dbg & 8)) v[i] = load_row4(p.src, p.Cin, p.vec4, idx[i], c0);
           }
           if (!waited) {  // the loads are in flight while the buffer drains
             WAIT(1, rce_bar(slot), ((q / p.nrc) & 1) ^ 1);
@@ -657,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         TL(4);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(rece_bar(rb));  // this warp no longer reads s_rec[rb]
+      if (lane == 0) mbar_arrive(ule_bar(ub));  // this warp no longer reads the list
     }
   } else if (warp < kMmaWarp0) {
     // ===================== builders: thread r owns tile slot r = TMEM lane r =====================
@@ -711,23 +721,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
             const uint32_t nu = min(us, nact - i * us);
             // unit 0: probe the stage's empty barrier, fetch this lane's row under the probe, then consume the probe
             const long long tw0 = DIAG ? clock64() : 0;
-            mbar_wait_and_load_row(aempty_bar(stage), phase ^ 1, v, rcb + loc0 * kRowStride, loc0 != 0xFFFFu && !(p.dbg & 2));
+            mbar_wait_and_load_row(aempty_bar(stage), phase ^ 1, v, rcb + loc0 * kRowStride, loc0 != 0xFFFFu && !(dbg & 2),
+                                   (uint32_t)p.wait_ns);
             if (DIAG) dg[2] += clock64() - tw0;
             TL(6);
             tc_fence_after();
             const long long ts0 = DIAG ? clock64() : 0;
-            if (!(p.dbg & 4)) tmem_st_row(t0, v);
+            if (!(dbg & 4)) tmem_st_row(t0, v);
             if (nu > 1) {
-              load_row(v, rcb + loc1 * kRowStride, loc1 != 0xFFFFu && !(p.dbg & 2));
-              if (!(p.dbg & 4)) tmem_st_row(t0 + kSlotCols, v);
+              load_row(v, rcb + loc1 * kRowStride, loc1 != 0xFFFFu && !(dbg & 2));
+              if (!(dbg & 4)) tmem_st_row(t0 + kSlotCols, v);
             }
             if (nu > 2) {
-              load_row(v, rcb + loc2 * kRowStride, loc2 != 0xFFFFu && !(p.dbg & 2));
-              if (!(p.dbg & 4)) tmem_st_row(t0 + 2 * kSlotCols, v);
+              load_row(v, rcb + loc2 * kRowStride, loc2 != 0xFFFFu && !(dbg & 2));
+              if (!(dbg & 4)) tmem_st_row(t0 + 2 * kSlotCols, v);
             }
             if (nu > 3) {
-              load_row(v, rcb + loc3 * kRowStride, loc3 != 0xFFFFu && !(p.dbg & 2));
-              if (!(p.dbg & 4)) tmem_st_row(t0 + 3 * kSlotCols, v);
+              load_row(v, rcb + loc3 * kRowStride, loc3 != 0xFFFFu && !(dbg & 2));
+              if (!(dbg & 4)) tmem_st_row(t0 + 3 * kSlotCols, v);
             }
             if (DIAG) dg[3] += clock64() - ts0;
             // row indices of this group's next stage (consumed one iteration later)
@@ -822,7 +833,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
             // fetched under the probe (the MMA takes its complement)
             uint4 vm;
             const long long tw0 = DIAG ? clock64() : 0;
-            mbar_wait_and_load16(afull_bar(stage), (Qi >> p.lna) & 1, vm, rec32 + 16 * k0);
+            mbar_wait_and_load16(afull_bar(stage), (Qi >> p.lna) & 1, vm, rec32 + 16 * k0, (uint32_t)p.wait_ns);
             if (DIAG) dg[2] += clock64() - tw0;
             TL(9);
             tc_fence_after();
@@ -835,7 +846,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
                 const uint32_t a = a_base + (stage * us + u) * kSlotCols;
                 const uint64_t bd =
                     desc0 + ((w_base + (p.resident ? (uint32_t)(k * KB + kb) : stage * us + u) * w_stage) >> 4);
-                if ((vm.x | vm.y | vm.z | vm.w) != 0 && !(p.dbg & 1)) {
+                if ((vm.x | vm.y | vm.z | vm.w) != 0 && !(dbg & 1)) {
                   if (NS == 2) {
                     const uint64_t bm = bd + (b_block >> 4);  // mid block
                     mma_ts(d, a, bd, idesc, off);
@@ -879,21 +890,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     const uint32_t rec0 = smem_u32(s_rec);
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t rb = it % p.nrec;
-      const int4 m = __ldg(p.meta + tile);
-      const uint32_t ub = (min(uni((uint32_t)m.y), (uint32_t)kRcap) * 4u + 15u) & ~15u;
       WAIT_RELAXED(0, rece_bar(rb), ((it / p.nrec) & 1) ^ 1);
       TL(12);
       if (elect_one()) {
-        mbar_expect_tx(recf_bar(rb), rec_main + ub);
-        const uint32_t dst = rec0 + rb * rec_buf;
-        bulk_g2s(dst, p.recs + tile * (int64_t)rec_main, rec_main, recf_bar(rb));
-        if (ub) bulk_g2s(dst + rec_main, p.uidx + tile * (int64_t)(kTileM * p.K), ub, recf_bar(rb));
+        mbar_expect_tx(recf_bar(rb), rec_main);
+        bulk_g2s(rec0 + rb * rec_buf, p.recs + tile * (int64_t)rec_main, rec_main, recf_bar(rb));
       }
       __syncwarp();
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;" ::: "memory");
-    if (!p.resident && warp < kWgtWarp0 + kWgtWarps) {
+    if (warp == kWgtWarp0 + kWgtWarps) {
+      // ===================== list producer: {nU} + the first kRcap unique rows of each tile, kUlSlots tiles ahead =====
+      uint32_t it = 0;
+      const uint32_t ul0 = smem_u32(s_ul);
+      for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t ub = it % kUlSlots;
+        const uint32_t rows = (min(uni((uint32_t)__ldg(&p.meta[tile].y)), (uint32_t)kRcap) * 4u + 15u) & ~15u;
+        WAIT_RELAXED(0, ule_bar(ub), ((it / kUlSlots) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(ulf_bar(ub), 16 + rows);
+          bulk_g2s(ul0 + ub * kUlBytes, p.recs + tile * (int64_t)rec_main + 16 * p.K, 16, ulf_bar(ub));  // header: nU first
+          if (rows) bulk_g2s(ul0 + ub * kUlBytes + 16, p.uidx + tile * (int64_t)(kTileM * p.K), rows, ulf_bar(ub));
+        }
+        __syncwarp();
+      }
+    } else if (!p.resident && warp < kWgtWarp0 + kWgtWarps) {
     // ===================== weight producers: bulk copy of each unit's pre-swizzled weight block into its stage =====
     const uint32_t wi = uni((uint32_t)(warp - kWgtWarp0));
     if (wi < (uint32_t)p.nwp) {
@@ -996,7 +1018,7 @@ static int plan_launch(wsis::umma::Params &p, int K, int Cin, int Cout, int NS, 
   const int64_t w_stage = 2 * (int64_t)Cout * 64, w_all = (int64_t)K * p.KB * w_stage;
   p.resident = w_all <= kResidentBytes;
   p.nwp = kWgtWarps;
-  const int64_t rec_buf = rec_stride_bytes(K) + kRcap * 4;
+  const int64_t rec_buf = rec_stride_bytes(K);
   // The ring holds at most `slots` operand slots; its throughput is slots / (round trip of a slot: TMEM store, hand-off,
   // MMA issue + execution, hand-off back), so all of them are used: stages x units per stage = slots (a power of two,
   // stages a multiple of the issuers and of the builder groups so that every stage has one owner of each kind).
@@ -1004,7 +1026,7 @@ static int plan_launch(wsis::umma::Params &p, int K, int Cin, int Cout, int NS, 
   int us_want = 1;
   if (const char *e = getenv("WSIS_CONV_US")) us_want = std::max(1, std::min(4, atoi(e)));
   int pool = slots >= 8 ? 8 : slots >= 4 ? 4 : 2;
-  static const int pref[][2] = {{3, 3}, {3, 2}, {2, 2}, {1, 2}, {1, 1}};  // {row-cache buffers, record buffers}
+  static const int pref[][2] = {{3, 3}, {2, 3}, {3, 2}, {2, 2}, {1, 2}, {1, 1}};  // {row-cache buffers, record buffers}
   const int64_t budget = 227 * 1024;
   int64_t smem = 0;
   bool fit = false;
@@ -1014,7 +1036,8 @@ static int plan_launch(wsis::umma::Params &p, int K, int Cin, int Cout, int NS, 
     if (us_ == 3) us_ = 2;
     const int na = pool / us_;
     for (auto &c : pref) {
-      const int64_t misc = 1024 /*align*/ + 2 * p.KB * cpu * 4 + (2 * na + 2 * c[0] + 2 * c[1] + 5) * 8 + 64;
+      const int64_t misc = 1024 /*align*/ + 2 * p.KB * cpu * 4 + (2 * na + 2 * c[0] + 2 * c[1] + 5 + 2 * kUlSlots) * 8 + 64 +
+                           kUlSlots * kUlBytes;
       smem = misc + (p.resident ? w_all : (int64_t)pool * w_stage) + c[0] * (int64_t)kRcBuf + c[1] * rec_buf;
       if (smem <= budget) {
         p.us = us_;
@@ -1117,8 +1140,14 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, c
     e = getenv("WSIS_CONV_DEBUG");
     p.dbg = e ? atoi(e) : 0;
   }
-  auto kern = g_diag ? (NS == 2 ? conv_umma_kernel<2, true> : conv_umma_kernel<1, true>)
-                     : (NS == 2 ? conv_umma_kernel<2, false> : conv_umma_kernel<1, false>);
+  void (*kern)(const Params) = nullptr;
+  const bool diag = g_diag != nullptr || p.dbg != 0;  // WSIS_CONV_DEBUG experiments run on the diagnostics build
+#define WSIS_PICK(NS_, US_) (diag ? conv_umma_kernel<NS_, US_, true> : conv_umma_kernel<NS_, US_, false>)
+  if (NS == 2)
+    kern = p.us == 1 ? WSIS_PICK(2, 1) : p.us == 2 ? WSIS_PICK(2, 2) : WSIS_PICK(2, 4);
+  else
+    kern = p.us == 1 ? WSIS_PICK(1, 1) : p.us == 2 ? WSIS_PICK(1, 2) : WSIS_PICK(1, 4);
+#undef WSIS_PICK
   // the opt-in is per device: set it on every launch rather than caching it process-wide (multi-GPU processes)
   WSIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sm_count());

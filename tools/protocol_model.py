@@ -58,7 +58,11 @@ class Cta(object):
         self.rcf = [Barrier(gather_warps) for _ in range(nrc)]
         self.rce = [Barrier(4 * nbg) for _ in range(nrc)]
         self.recf = [Barrier(1) for _ in range(nrec)]
-        self.rece = [Barrier(gather_warps + 4 * nbg + nmma) for _ in range(nrec)]
+        self.rece = [Barrier(4 * nbg + nmma) for _ in range(nrec)]
+        self.nul = 4                                                       # ring of unique-row lists (gatherers)
+        self.ulf = [Barrier(1) for _ in range(self.nul)]
+        self.ule = [Barrier(gather_warps) for _ in range(self.nul)]
+        self.ul = [None] * self.nul
         self.accf = [Barrier(nmma) for _ in range(2)]
         self.acce = [Barrier(epi_warps) for _ in range(2)]
         # buffer contents (what the consumer must find)
@@ -81,6 +85,14 @@ class Cta(object):
             yield
             self.recf[rb].arrive()                                         # expect_tx arrive + bytes landed
 
+    def list_producer(self):
+        for it in range(len(self.tiles)):
+            ub = it % self.nul
+            yield from wait(self.ule[ub], ((it // self.nul) & 1) ^ 1, it // self.nul, "list buffer free")
+            self.ul[ub] = it
+            yield
+            self.ulf[ub].arrive()
+
     def weight_producer(self, wi):
         if self.resident:
             return
@@ -98,10 +110,10 @@ class Cta(object):
     def gatherer(self, g):
         q = 0
         for it, (nact, KB) in enumerate(self.tiles):
-            rb = it % self.nrec
-            yield from wait(self.recf[rb], (it // self.nrec) & 1, it // self.nrec + 1, "record ready (gatherer)")
-            if self.rec[rb] != it:
-                raise ProtocolError("gatherer reads record of tile %s, wants %d" % (self.rec[rb], it))
+            ub = it % self.nul
+            yield from wait(self.ulf[ub], (it // self.nul) & 1, it // self.nul + 1, "list ready (gatherer)")
+            if self.ul[ub] != it:
+                raise ProtocolError("gatherer reads list of tile %s, wants %d" % (self.ul[ub], it))
             for _ in range(KB):
                 slot = q % self.nrc
                 yield                                                       # loads in flight
@@ -111,7 +123,7 @@ class Cta(object):
                 yield
                 self.rcf[slot].arrive()
                 q += 1
-            self.rece[rb].arrive()
+            self.ule[ub].arrive()
 
     def builder(self, bw):
         g, w4 = bw // 4, bw % 4
@@ -187,7 +199,7 @@ class Cta(object):
 
     def run(self, seed=0, max_steps=10 ** 7):
         rng = random.Random(seed)
-        roles = [self.record_producer()] + [self.weight_producer(w) for w in range(self.nwp)]
+        roles = [self.record_producer(), self.list_producer()] + [self.weight_producer(w) for w in range(self.nwp)]
         roles += [self.gatherer(g) for g in range(self.G)]
         roles += [self.builder(b) for b in range(4 * self.nbg)]
         roles += [self.issuer(m) for m in range(self.nmma)]
@@ -216,7 +228,7 @@ class Cta(object):
         return True
 
     def _state(self):
-        bars = self.afull + self.aempty + self.rcf + self.rce + self.recf + self.rece + self.accf + self.acce
+        bars = self.afull + self.aempty + self.rcf + self.rce + self.recf + self.rece + self.accf + self.acce + self.ulf + self.ule
         return tuple((b.phase, b.pending) for b in bars) + (len(self.done_stages),)
 
 

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256, 1) pingpong_kernel(int mode, int rounds, 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int e = tid; e < 4096; e += blockDim.x) reinterpret_cast<uint32_t *>(sB)[e] = 0;
   if (tid == 0) {
-    mbar_init(smem_u32(bars + 0), 1);
+    mbar_init(smem_u32(bars + 0), mode >= 3 ? 4 : 1);
     mbar_init(smem_u32(bars + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -316,7 +316,37 @@ __global__ void __launch_bounds__(256, 1) pingpong_kernel(int mode, int rounds, 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tb = *s_tmem;
   const uint32_t b0 = smem_u32(bars + 0), b1 = smem_u32(bars + 1);
-  if (warp == 0) {
+  if (mode >= 3) {
+    // modes 3..5: warps 0-3 are a builder group (b0 counts their 4 arrivals), warp 4 the issuer.
+    //   3: fences only; 4: + tcgen05.wait::st; 5: + a 32-column tcgen05.st per round
+    if (warp < 4) {
+      const uint32_t taddr = tb + ((uint32_t)(warp * 32) << 16) + 384;
+      __syncwarp();
+      const long long t0 = clock64();
+      for (int r = 0; r < rounds; ++r) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (mode >= 5)
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,"
+              "%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"((uint32_t)r)
+              : "memory");
+        if (mode >= 4) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b0) : "memory");
+        mbar_wait(b1, r & 1);
+      }
+      const long long t1 = clock64();
+      if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    } else if (warp == 4) {
+      for (int r = 0; r < rounds; ++r) {
+        mbar_wait(b0, r & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) mma_commit(b1);
+        __syncwarp();
+      }
+    }
+  } else if (warp == 0) {
     __syncwarp();
     const long long t0 = clock64();
     for (int r = 0; r < rounds; ++r) {
@@ -424,7 +454,7 @@ int main() {
            median(st) / units);
   }
   // ---- hand-off round trips ----
-  for (int mode = 0; mode < 3; ++mode) {
+  for (int mode = 0; mode < 6; ++mode) {
     const int rounds = 2000;
     pingpong_kernel<<<grid, 256, smem>>>(mode, rounds, d_cyc);
     pingpong_kernel<<<grid, 256, smem>>>(mode, rounds, d_cyc);
@@ -432,7 +462,7 @@ int main() {
     CK(cudaMemcpy(h.data(), d_cyc, sizeof(long long) * grid, cudaMemcpyDeviceToHost));
     std::vector<long long> rt(h.begin(), h.begin() + grid);
     printf("{\"pingpong\": \"%s\", \"cyc_per_round_trip\": %.1f}\n",
-           mode == 0 ? "arrive <-> arrive" : mode == 1 ? "arrive <-> tcgen05.commit (idle pipe)" : "arrive <-> one N=32 MMA + commit",
+           mode == 0 ? "arrive <-> arrive" : mode == 1 ? "arrive <-> tcgen05.commit (idle pipe)" : mode == 2 ? "arrive <-> one N=32 MMA + commit" : mode == 3 ? "4 warps {fences, arrive} <-> commit" : mode == 4 ? "4 warps {fences, wait::st, arrive} <-> commit" : "4 warps {tcgen05.st.x32, wait::st, fences, arrive} <-> commit",
            median(rt) / rounds);
   }
   return 0;
