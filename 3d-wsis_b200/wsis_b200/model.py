@@ -345,6 +345,8 @@ class Network(nn.Module):
         edge_u_list), "num_superpoints"."""
         ret = {}
         output = self.output_layer(self.unet(self.input_conv(input)))
+        if extra_data.get("keep_unet_features"):      # parity checks compare the U-Net output itself
+            extra_data["unet_features"] = output.features
         fused = not torch.is_grad_enabled() and not self.training and output.features.is_cuda
 
         superpoint = extra_data["superpoint"].long()

@@ -45,7 +45,7 @@ def to_device(batch, device="cuda", non_blocking=True):
     return out, nbytes
 
 
-def forward_batch(model, dbatch, use_coords=True, mode=4):
+def forward_batch(model, dbatch, use_coords=True, mode=4, keep_unet_features=False):
     """Voxelization + UNet + pooling + affinity for one device-resident batch.  Returns (ret dict, aux dict)."""
     locs = dbatch["locs"]
     S = dbatch["num_superpoints"]
@@ -60,14 +60,15 @@ def forward_batch(model, dbatch, use_coords=True, mode=4):
     eindex = W.SegmentIndex(dbatch["edge_u_list"], S)
     extra = {"superpoint": superpoint, "GIs": [GraphInfo(dbatch["ecc_edge_index"], dbatch["ecc_edgefeats"])],
              "edge_u_list": dbatch["edge_u_list"], "edge_v_list": dbatch["edge_v_list"],
-             "superpoint_cenetr_xyz": centers, "sp_index": sp_index, "edge_index_u": eindex, "num_superpoints": S}
+             "superpoint_cenetr_xyz": centers, "sp_index": sp_index, "edge_index_u": eindex, "num_superpoints": S,
+             "keep_unet_features": keep_unet_features}
     if torch.is_grad_enabled() or model.training:
         ret = model(input_, p2v_map, extra)
     else:
         with spconv.ops.lazy_pairs():  # inference: nothing reads the reference-format pair tensors
             ret = model(input_, p2v_map, extra)
     aux = {"voxel_locs": voxel_locs, "p2v_map": p2v_map, "v2p_map": v2p_map, "centers": centers, "input": input_,
-           "edge_index_u": eindex}
+           "edge_index_u": eindex, "unet_features": extra.get("unet_features")}
     return ret, aux
 
 

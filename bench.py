@@ -149,39 +149,54 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------------------------
-def cpu_pass(args, n_steps, warmup):
-    """The reference's CPU path on the host cores, bounded sample = `cpu_sample_scenes` scene(s) per step."""
+def cpu_pass(args, n_steps, warmup, sample_scenes=None, want_parity=None):
+    """The reference's CPU path on the host cores: `warmup` untimed + `n_steps` timed steps, each over a bounded sample
+    of `sample_scenes` scene(s) of the workload's batch (seeds 2000, 2001, ...: the first scenes of the device arm's
+    batch 0).  value = scenes / wall time of the timed steps (not best-of).  `want_parity` (a dict) receives the last
+    step's outputs and rulebooks for the device-vs-reference comparison."""
     from oracle import cpu_pipeline
     from wsis_b200 import pipeline, synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    n_sc = sample_scenes or args.cpu_sample_scenes
     net = pipeline.build_network(seed=123, device="cpu").eval()
     mk = synthetic.make_room_s3dis if args.shape == "s3dis" else synthetic.make_scene
-    scenes = [mk(2000 + i, n_points=args.points) for i in range(args.cpu_sample_scenes)]
-    batch = synthetic.collate(scenes)
-    times, stages, kind = [], None, "port"
+    batch = synthetic.collate([mk(2000 + i, n_points=args.points) for i in range(n_sc)])
+    times, stages, kind, ret, keep = [], None, "port", None, {}
     for it in range(warmup + n_steps):
+        keep = {} if want_parity is not None else None
         t0 = time.perf_counter()
-        _, stages, kind = cpu_pipeline.forward(net, batch)
+        ret, stages, kind = cpu_pipeline.forward(net, batch, keep=keep)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    best = min(times)
-    return {"value": args.cpu_sample_scenes / best, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d scene(s) of %d pts, full hot path, best of %d after %d warm-up; threads=%d; stages(s)=%s"
-                      % (args.cpu_sample_scenes, args.points, n_steps, warmup, cores,
-                         {k: round(v, 3) for k, v in stages.items()}),
-            "ms_per_step": 1e3 * best}
+    if want_parity is not None:
+        want_parity.update(ret=ret, keep=keep, batch=batch)
+    total = sum(times)
+    return {"value": n_sc * n_steps / total, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d scene(s) of %d pts per step (of the %d-scene batch), full hot path, %d timed steps after %d "
+                      "warm-up, mean; threads=%d; stages(s)=%s"
+                      % (n_sc, args.points, args.scenes, n_steps, warmup, cores, {k: round(v, 3) for k, v in stages.items()}),
+            "ms_per_step": 1e3 * total / n_steps, "ms_per_step_min_max": [round(1e3 * min(times), 1), round(1e3 * max(times), 1)],
+            "scenes_per_step": n_sc, "steps": n_steps, "warmup": warmup}
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU kernels (oracle/_ref) on the host cores, EXACTLY `--steps` timed and
+    `--warmup` untimed steps.  A step is the full batch of the device arm when ~1.2 s per scene lets the whole run end
+    within about three minutes, otherwise a bounded sample of it (and the line says which)."""
     if rank != 0:
         return
-    cb = cpu_pass(args, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    est_scene_s = 1.3 * args.points / 150000.0
+    budget_s = 170.0
+    n_sc = max(1, min(args.scenes, int(budget_s / max(est_scene_s * (args.steps + args.warmup), 1e-9))))
+    cb = cpu_pass(args, args.steps, args.warmup, sample_scenes=n_sc)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"] , "higher_is_better": True,
+            "steps": cb["steps"], "warmup": cb["warmup"], "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, {"note": "reference CPU path on host cores; each step is a bounded sample "
-                                                      "of %d scene(s) of the workload" % args.cpu_sample_scenes}),
+            "config": workload_config(args, {"note": "reference CPU path (unmodified spconv CPU kernels, oracle/_ref) on "
+                                                      "the host cores; each step covers %d of the batch's %d scene(s)"
+                                                      % (n_sc, args.scenes), "scenes_per_step": n_sc,
+                                             "l2": "n/a (host)"}),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -235,31 +250,68 @@ def conv_roofline(net, dbatch, pipeline, W, steps, peaks):
     # dominant kernel = the layer shape (Cin, Cout, K, rows) whose launches take the largest share of the step
     groups = {}
     for i, (_, b, f, shp) in enumerate(last):
-        g = groups.setdefault(shp, {"idx": [], "bytes": b, "flops": f})
+        g = groups.setdefault(shp, {"idx": [], "bytes": 0, "flops": f})
         g["idx"].append(i)
+        g["bytes"] += b
+    for g in groups.values():
+        g["bytes"] /= len(g["idx"])  # mean over the group's launches (some fuse the residual read, some do not)
     for g in groups.values():
         g["t"] = statistics.mean(sum(st[i][0] for i in g["idx"]) for st in per_step)
     shp, g = max(groups.items(), key=lambda kv: kv[1]["t"])
     t_launch = g["t"] / len(g["idx"])
     ach = g["bytes"] / t_launch / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_ncu_conv_umma_v3.json")
+    # `traffic` cannot be measured inside a timed run (it needs ncu counters): it is read from the committed
+    # `ncu --set full` capture of this kernel on this layer shape, and `traffic_source` says so; null when the capture
+    # is of another shape
+    traffic, traffic_source = None, None
+    prof = os.path.join(ROOT, "profiles", "r02_ncu_conv_umma_v4.json")
     if os.path.exists(prof):
         pj = json.load(open(prof))
-        if list(pj.get("cin_cout_K_rows", [])) == list(shp):  # same layer shape, same rows: per-launch DRAM bytes
+        if list(pj.get("cin_cout_K_rows", [])) == list(shp):
             traffic = pj.get("dram_bytes_per_launch")
+            traffic_source = "profiles/r02_ncu_conv_umma_v4.json (ncu --set full of one launch of this layer shape, " \
+                             "not measured in this run)"
     ach_all = bsum / tsum / 1e9
     return {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic,
+            "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": traffic, "traffic_source": traffic_source,
             "kernel": "conv_umma_kernel, layer shape (Cin, Cout, K, rows) = %s: %d launches per step, %.1f%% of the "
                       "step's sparse-conv time" % (list(shp), len(g["idx"]), 100.0 * g["t"] / tsum),
-            "algorithmic_bytes_per_launch": g["bytes"], "us_per_launch": round(t_launch * 1e6, 1),
+            "algorithmic_bytes_per_launch": int(g["bytes"]), "us_per_launch": round(t_launch * 1e6, 1),
             "useful_tflops": round(g["flops"] / t_launch / 1e12, 1),
             "all_sparse_conv": {"launches_per_step": nl, "algorithmic_bytes_per_step": bsum,
                                 "ms_per_step": round(tsum * 1e3, 3), "GBps": round(ach_all, 1),
                                 "frac": round(ach_all / peaks["hbm_gbs"], 4),
                                 "useful_tflops": round(fsum / tsum / 1e12, 1)},
             "peak_source": peaks["source"]}
+
+
+def count_all_launches(step):
+    """Every kernel launch of one step, the library's own and torch's, counted by the CUDA profiler outside the timed
+    region (gpu_launches counts only this repo's kernels)."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        return sum(1 for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
+                   and not e.name.lower().startswith("memcpy") and not e.name.lower().startswith("memset"))
+    except Exception as e:  # noqa: BLE001  (profiler unavailable: say so instead of guessing)
+        return "unavailable: %s" % type(e).__name__
+
+
+def device_vs_reference(net, got, pipeline, precision):
+    """The device path against the reference's CPU kernels on the cpu_baseline's sample scenes (same seeds, same
+    weights): rulebooks as sorted pair sets, voxelization maps, U-Net output and every result tensor."""
+    from oracle import parity
+    dbatch, _ = pipeline.to_device(got["batch"])
+    with torch.no_grad():
+        ret, aux = pipeline.forward_batch(net, dbatch, keep_unet_features=True)
+    res = parity.compare(ret, aux, got["ret"], got["keep"])
+    return {"rulebooks_equal": res["rulebooks_equal"], "rulebook_pairs": {k: v["pairs"] for k, v in res["rulebooks"].items()},
+            "voxelization_equal": res["voxelization_equal"], "max_rel": res["max_rel"],
+            "max_rel_per_output": {k: float("%.3g" % v) for k, v in res["outputs"].items()},
+            "against": "reference spconv CPU kernels (oracle/_ref) on %d scene(s); tolerance %s"
+                       % (got["batch"]["batch_size"], "1e-4" if precision == "fp32" else "1e-2 (bf16 operands)")}
 
 
 def load_peaks():
@@ -347,12 +399,16 @@ def run_ours(args, rank, world, local_rank):
     t_end = time.time()
     t_e2e, _, io, ms_e2e = timed(step_e2e, args.steps, args.warmup)
 
-    roof = cpu = None
+    roof = cpu = parity_obj = None
+    launches_total = None
     if rank == 0:
         roof = conv_roofline(net, dev[0], pipeline, W, max(2, min(args.steps, 5)), peaks)
+        launches_total = count_all_launches(lambda: step_resident(0))
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_pass(args, 2, 1)
+            got = {}
+            cb = cpu_pass(args, 2, 1, want_parity=got)
             cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            parity_obj = device_vs_reference(net, got, pipeline, args.precision)
     clocks.terminate()
     clk = clocks.summary(t_begin, t_end)
     if rank == 0:
@@ -371,7 +427,8 @@ def run_ours(args, rank, world, local_rank):
                         "ms_per_step": 1e3 * t_e2e / args.steps,
                         "ms_per_step_min_median_max": [round(min(ms_e2e), 3), round(statistics.median(ms_e2e), 3),
                                                        round(max(ms_e2e), 3)]},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+                "launches_total_per_step": launches_total, "roofline": roof, "cpu_baseline": cpu, "parity": parity_obj}
         print(json.dumps(line), flush=True)
 
 

@@ -103,9 +103,11 @@ def _scatter(src, index, reduce, S):
 
 
 @torch.no_grad()
-def forward(net, batch, prefer_reference=True):
+def forward(net, batch, prefer_reference=True, keep=None):
     """CPU forward of one collated batch with `net` (a CPU, eval-mode wsis_b200.model.Network).
-    Returns (ret dict of torch CPU tensors, stage timings dict, kind)."""
+    Returns (ret dict of torch CPU tensors, stage timings dict, kind).  When `keep` is a dict it receives what the
+    parity checks compare besides the outputs: the nine rulebooks (key -> (in coords, out coords, pairs, num)), the
+    voxelization maps and the U-Net output features."""
     sp = CpuSpconv(prefer_reference)
     T = {}
     t0 = time.perf_counter()
@@ -127,6 +129,8 @@ def forward(net, batch, prefer_reference=True):
     x = _bn_relu(list(net.output_layer._modules.values())[0], x)
     T["unet"] = time.perf_counter() - t0
     T["unet_rulebooks"], T["unet_convs"] = sp.t_rulebook, sp.t_conv
+    if keep is not None:
+        keep.update(rulebooks=dict(sp.rulebooks), voxel_locs=voxel_locs, p2v=p2v, v2p=v2p, unet_out=x)
     t0 = time.perf_counter()
     output_feats = x[p2v.long()]
     ret = {"semantic_scores": net.linear(output_feats)}

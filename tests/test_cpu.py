@@ -437,11 +437,14 @@ def test_gloo_world2_sharding_and_gradient_allreduce(tmp_path):
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` prints one JSON line with the agreed keys (bounded sample, CPU only)."""
     import json
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--points", "20000"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--points", "20000", "--scenes", "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["impl"] == "reference" and line["unit"] == "scenes/s" and line["value"] > 0
+    # the line reports the steps it really ran, each over the whole (small) batch: value = scenes / time
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["config"]["scenes_per_step"] == 2
+    assert abs(line["value"] - 2 / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
 
