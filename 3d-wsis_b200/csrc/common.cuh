@@ -91,8 +91,8 @@ __device__ __forceinline__ int64_t hash_find(const unsigned long long *__restric
 }
 
 // tile record geometry (tilemap.cu builds the records, conv_umma.cu consumes them)
-//   valid[K][4] u32 | {nU u32, amask u32, P u32, nact u32, klist u8[32]} | loc[K][128] u16
-__host__ __device__ __forceinline__ int rec_hdr_bytes(int K) { return 16 * K + 48; }
+//   valid[K][4] u32 | {nU u32, amask u32, P u32, npack u32, members u16[32]} | loc[K][128] u16
+__host__ __device__ __forceinline__ int rec_hdr_bytes(int K) { return 16 * K + 80; }
 __host__ __device__ __forceinline__ int rec_stride_bytes(int K) { return rec_hdr_bytes(K) + 256 * K; }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -48,6 +48,10 @@
 
 #include "common.cuh"
 
+#ifndef WSIS_KO
+#define WSIS_KO 0
+#endif
+
 namespace wsis {
 namespace umma {
 
@@ -447,8 +451,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t rec_main = (uint32_t)rec_stride_bytes(p.K);
   const uint32_t rec_buf = rec_main;
   constexpr uint32_t us = US;  // units per stage
-  const int dbg = DIAG ? p.dbg : 0;  // timing experiments exist in the diagnostics build only
-  const uint32_t w_bytes = p.resident ? (uint32_t)(p.K * KB) * w_stage : na * us * w_stage;
+  // timing experiments: run-time switches in the diagnostics build; the product build can be compiled with a fixed set
+  // (-DWSIS_KO=bits, tools/gpu_knockout.sh) so that the experiment runs on product-quality code
+  const int dbg = DIAG ? p.dbg : WSIS_KO;
+  const uint32_t w_bytes = p.resident ? (uint32_t)(p.K * KB) * w_stage : na * us * 2 * w_stage;  // two members per unit
   uint8_t *s_w = sm;                                   // weight blocks: ring of na stages, or the whole packed weight
   uint8_t *s_rc = s_w + w_bytes;                       // [nrc][kRcap][128 B]   converted source rows
   uint8_t *s_rec = s_rc + (size_t)p.nrc * kRcBuf;      // [nrec][rec_buf]       tile records (bulk copies)
@@ -470,7 +476,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
   const uint32_t wres_bar = bar2 + 8u * (2 * p.nrec + 4);
   auto ulf_bar = [&](uint32_t s) { return wres_bar + 8u * (1 + s); };
   auto ule_bar = [&](uint32_t s) { return wres_bar + 8u * (1 + kUlSlots + s); };
-  const uint32_t nbars = 2 * na + 2 * p.nrc + 2 * p.nrec + 5 + 2 * kUlSlots;
+  auto rawf_bar = [&](uint32_t s) { return wres_bar + 8u * (1 + 2 * kUlSlots + s); };  // raw rows landed (bulk copies)
+  const uint32_t nbars = 2 * na + 3 * p.nrc + 2 * p.nrec + 5 + 2 * kUlSlots;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + nbars);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -499,6 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     for (int s = 0; s < p.nrc; ++s) {
       mbar_init(rcf_bar(s), kGatherWarps);
       mbar_init(rce_bar(s), kBuildWarps);
+      mbar_init(rawf_bar(s), kGatherWarps);
     }
     for (int s = 0; s < p.nrec; ++s) {
       mbar_init(recf_bar(s), 1);
@@ -563,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       float4 r4[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) r4[q] = has_res ? __ldg(rs + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      WAIT_RELAXED(0, accf_bar(as), aph);
+      WAIT(0, accf_bar(as), aph);
       TL(1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * acc_cols;
@@ -613,6 +621,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
     constexpr int LPR = CPU / 4;  // lanes per row: each lane converts 4 channels
     const int gt = (warp - kGatherWarp0) * 32 + lane;
     const int rsub = gt / LPR, chunk = gt % LPR;
+    constexpr int kInFlight = 8;  // 16-byte register loads in flight per gather lane (the non-bulk path)
+    const bool bulk_rows = p.vec4 && (p.Cin % CPU) == 0;
     uint32_t it = 0, q = 0;
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       // the tile's list of distinct rows comes through its own small ring, several tiles ahead of the (large) record
@@ -632,7 +642,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         uint8_t *rcb = s_rc + (size_t)slot * kRcBuf;
         bool waited = false;
         constexpr int kSweep = kGatherWarps * 32 / LPR;  // rows per load instruction of the gather warps
-        constexpr int kInFlight = 8;                     // 16-byte loads in flight per gather lane
+        if (NS == 2 && bulk_rows) {
+          // ---- fp32 contract, 16-byte aligned rows of whole 32-channel blocks: the raw 128-byte row slices are
+          // copied global -> row cache by cp.async (ALL rows of the pass in flight at once, no registers held, one
+          // round trip of latency per pass instead of one per batch of 8 register loads; 128-byte cp.async.bulk
+          // copies were slower: ~46 cycles of the copy engine each) and converted in place: a row's eight lanes read
+          // their 16 bytes of fp32, then write 8 bytes of hi and 8 bytes of mid ----
+          WAIT(1, rce_bar(slot), ((q / p.nrc) & 1) ^ 1);
+          waited = true;
+          if (!(dbg & 8)) {
+            // every lane copies ITS 16-byte chunk of each of its rows and later converts exactly those bytes, so the
+            // per-thread completion of cp.async is all the ordering the conversion needs
+            for (int u = rsub; u < ng; u += kSweep) {
+              const float *g = p.src + (int64_t)uidx[u] * p.Cin + c0;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(rcb) + (uint32_t)u * kRowStride +
+                                                                              (uint32_t)chunk * 16u),
+                           "l"(g)
+                           : "memory");
+            }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+          }
+          for (int u0 = 0; u0 < ng && !(dbg & 32); u0 += 4 * kSweep) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int u = u0 + i * kSweep + rsub;
+              if (u < ng) v[i] = *reinterpret_cast<const float4 *>(rcb + (size_t)u * kRowStride + chunk * 16);
+            }
+            __syncwarp();  // every lane of a row has read its 16 raw bytes before any of them overwrites the row
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int u = u0 + i * kSweep + rsub;
+              if (u < ng) {
+                const float4 y = prologue4(v[i], sc, sh, p.in_relu);
+                uint8_t *r = rcb + (size_t)u * kRowStride + chunk * 8;
+                *reinterpret_cast<uint2 *>(r) = make_uint2(split2(y.x, y.y, 0), split2(y.z, y.w, 0));
+                *reinterpret_cast<uint2 *>(r + 64) = make_uint2(split2(y.x, y.y, 1), split2(y.z, y.w, 1));
+              }
+            }
+          }
+        } else
         for (int u0 = 0; u0 < ng && !(dbg & 32); u0 += kInFlight * kSweep) {
           int32_t idx[kInFlight];
           float4 v[kInFlight];
@@ -695,9 +744,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       const uint32_t rb = it % p.nrec;
       WAIT(0, recf_bar(rb), (it / p.nrec) & 1);
       const uint32_t rec32 = s_rec32 + rb * rec_buf;
-      const uint32_t nact = lds32(rec32 + hdr_off + 12);
+      const uint32_t nact = lds32(rec32 + hdr_off + 12);  // packs of the tile (units of one pass)
       const bool big = lds32(rec32 + hdr_off) > (uint32_t)kRcap;  // more distinct rows than a row-cache buffer holds
-      const uint32_t locs32 = rec32 + hdr_off + 48 + slot_r * 2;  // loc row of the i-th active offset at + 256 i
+      const uint32_t locs32 = rec32 + hdr_off + 80 + slot_r * 2;  // loc row of the i-th pack at + 256 i
       const uint32_t nq = (nact + us - 1) / us;                    // stages of one pass
       for (int kb = 0; kb < KB; ++kb, ++q) {
         const uint32_t slot = q % p.nrc;
@@ -814,8 +863,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         const uint32_t rb = it % p.nrec;
         WAIT(0, recf_bar(rb), (it / p.nrec) & 1);
         const uint32_t rec32 = smem_u32(s_rec) + rb * rec_buf;
-        const uint32_t nact = uni(lds32(rec32 + hdr_off + 12));
-        const uint32_t kl = lds_u8(rec32 + hdr_off + 16 + (uint32_t)lane);  // lane l: the l-th active offset
+        const uint32_t nact = uni(lds32(rec32 + hdr_off + 12));               // packs of the tile
+        const uint32_t kl = lds_u16(rec32 + hdr_off + 16 + 2u * (uint32_t)lane);  // lane l: members of pack l
         const uint32_t nq = (nact + us - 1) / us;
         WAIT(1, acce_bar(as), aph ^ 1);
         TL(8);
@@ -824,44 +873,53 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
         for (int kb = 0; kb < KB; ++kb) {
           // 16-channel K steps of this unit that hold real channels
           const int ksteps = min(CPU / 16, (p.Cin - kb * CPU + 15) / 16);
-          // stage Q of the CTA belongs to issuer Q mod nmma, who issues all of its units into its own accumulator
+          // stage Q of the CTA belongs to issuer Q mod nmma, who issues all of its units into its own accumulator.
+          // A unit is a PACK: one operand block, multiplied once per member offset with that member's lane mask and
+          // weight block.
           for (uint32_t i = (mi - Q) & (nmma - 1); i < nq; i += nmma) {
             const uint32_t Qi = Q + i, stage = Qi & (na - 1);
             const uint32_t nu = min(us, nact - i * us);
-            const uint32_t k0 = __shfl_sync(0xffffffffu, kl, (int)((i * us) & 31u));
-            // operand rows (tcgen05.st, fenced by the builders) + weights; the valid-slot mask of the first unit is
+            const uint32_t mem0 = __shfl_sync(0xffffffffu, kl, (int)((i * us) & 31u));
+            // operand rows (tcgen05.st, fenced by the builders) + weights; the valid-slot mask of the first member is
             // fetched under the probe (the MMA takes its complement)
             uint4 vm;
             const long long tw0 = DIAG ? clock64() : 0;
-            mbar_wait_and_load16(afull_bar(stage), (Qi >> p.lna) & 1, vm, rec32 + 16 * k0, (uint32_t)p.wait_ns);
+            mbar_wait_and_load16(afull_bar(stage), (Qi >> p.lna) & 1, vm, rec32 + 16 * (mem0 & 0xFFu) * ((mem0 & 0xFFu) != 0xFFu),
+                                 (uint32_t)p.wait_ns);
             if (DIAG) dg[2] += clock64() - tw0;
             TL(9);
             tc_fence_after();
             const long long ti0 = DIAG ? clock64() : 0;
             for (uint32_t u = 0; u < nu; ++u) {
-              const uint32_t k = u == 0 ? k0 : __shfl_sync(0xffffffffu, kl, (int)((i * us + u) & 31u));
+              const uint32_t mem = u == 0 ? mem0 : __shfl_sync(0xffffffffu, kl, (int)((i * us + u) & 31u));
               if (elect_one()) {
-                if (u) vm = lds128(rec32 + 16 * k);
-                const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
                 const uint32_t a = a_base + (stage * us + u) * kSlotCols;
-                const uint64_t bd =
-                    desc0 + ((w_base + (p.resident ? (uint32_t)(k * KB + kb) : stage * us + u) * w_stage) >> 4);
-                if ((vm.x | vm.y | vm.z | vm.w) != 0 && !(dbg & 1)) {
-                  if (NS == 2) {
-                    const uint64_t bm = bd + (b_block >> 4);  // mid block
-                    mma_ts(d, a, bd, idesc, off);
-                    mma_ts(d, a, bm, idesc, off);
-                    mma_ts(d, a + 16, bd, idesc, off);
-                    if (ksteps > 1) {
-                      mma_ts(d, a + 8, bd + 2, idesc, off);
-                      mma_ts(d, a + 8, bm + 2, idesc, off);
-                      mma_ts(d, a + 24, bd + 2, idesc, off);
+#pragma unroll
+                for (uint32_t m = 0; m < 2; ++m) {
+                  const uint32_t k = (mem >> (8 * m)) & 0xFFu;
+                  if (k != 0xFFu) {
+                    if (u || m) vm = lds128(rec32 + 16 * k);
+                    const uint4 off = make_uint4(~vm.x, ~vm.y, ~vm.z, ~vm.w);
+                    const uint64_t bd = desc0 + ((w_base + (p.resident ? (uint32_t)(k * KB + kb)
+                                                                       : (stage * us + u) * 2 + m) * w_stage) >> 4);
+                    if (!(dbg & 1)) {
+                      if (NS == 2) {
+                        const uint64_t bm = bd + (b_block >> 4);  // mid block
+                        mma_ts(d, a, bd, idesc, off);
+                        mma_ts(d, a, bm, idesc, off);
+                        mma_ts(d, a + 16, bd, idesc, off);
+                        if (ksteps > 1) {
+                          mma_ts(d, a + 8, bd + 2, idesc, off);
+                          mma_ts(d, a + 8, bm + 2, idesc, off);
+                          mma_ts(d, a + 24, bd + 2, idesc, off);
+                        }
+                      } else {
+                        mma_ts(d, a, bd, idesc, off);
+                        if (ksteps > 1) mma_ts(d, a + 8, bd + 2, idesc, off);
+                        if (ksteps > 2) mma_ts(d, a + 16, bd + (b_block >> 4), idesc, off);
+                        if (ksteps > 3) mma_ts(d, a + 24, bd + (b_block >> 4) + 2, idesc, off);
+                      }
                     }
-                  } else {
-                    mma_ts(d, a, bd, idesc, off);
-                    if (ksteps > 1) mma_ts(d, a + 8, bd + 2, idesc, off);
-                    if (ksteps > 2) mma_ts(d, a + 16, bd + (b_block >> 4), idesc, off);
-                    if (ksteps > 3) mma_ts(d, a + 24, bd + (b_block >> 4) + 2, idesc, off);
                   }
                 }
                 if (u + 1 == nu) mma_commit(aempty_bar(stage));
@@ -923,24 +981,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const Params p) 
       const uint32_t w_base = smem_u32(s_w);
       const uint32_t nwp = (uint32_t)p.nwp;  // a power of two
       for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const uint32_t nact = uni((uint32_t)__popc((uint32_t)__ldg(&p.meta[tile].z)));
-        const uint32_t kl = __ldg(p.recs + tile * (int64_t)rec_main + 16 * p.K + 16 + lane);  // the record's klist
+        const uint32_t nact = uni((uint32_t)__ldg(&p.meta[tile].z));  // packs of the tile
+        // lane l: members of pack l (the record's header, read from global memory: the producers run ahead of the ring)
+        const uint32_t kl = __ldg(reinterpret_cast<const uint16_t *>(p.recs + tile * (int64_t)rec_main + 16 * p.K + 16) + lane);
         const uint32_t nq = (nact + us - 1) / us;
         for (int kb = 0; kb < KB; ++kb) {
           for (uint32_t i = (wi - Q) & (nwp - 1); i < nq; i += nwp) {
             const uint32_t Qi = Q + i, sw = Qi & (na - 1);
             const uint32_t nu = min(us, nact - i * us);
-            uint32_t ku[4];
+            uint32_t mu[4];
 #pragma unroll
-            for (uint32_t u = 0; u < 4; ++u) ku[u] = __shfl_sync(0xffffffffu, kl, (int)((i * us + u) & 31u));
+            for (uint32_t u = 0; u < 4; ++u) mu[u] = __shfl_sync(0xffffffffu, kl, (int)((i * us + u) & 31u));
             WAIT(0, aempty_bar(sw), ((Qi >> p.lna) & 1) ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(afull_bar(sw), nu * w_stage);
+              uint32_t nblk = 0;
 #pragma unroll
               for (uint32_t u = 0; u < 4; ++u)
-                if (u < nu)
-                  bulk_g2s(w_base + (sw * us + u) * w_stage, p.packed + (size_t)(ku[u] * KB + kb) * w_stage, w_stage,
-                           afull_bar(sw));
+                if (u < us && u < nu) nblk += ((mu[u] & 0xFFu) != 0xFFu) + ((mu[u] >> 8) != 0xFFu);
+              if (nblk == 0) {
+                mbar_arrive(afull_bar(sw));  // a tile without entries: the dummy unit has no weights
+              } else {
+                mbar_expect_tx(afull_bar(sw), nblk * w_stage);
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u)
+                  if (u < us && u < nu) {
+#pragma unroll
+                    for (uint32_t m = 0; m < 2; ++m) {
+                      const uint32_t k = (mu[u] >> (8 * m)) & 0xFFu;
+                      if (k != 0xFFu)
+                        bulk_g2s(w_base + ((sw * us + u) * 2 + m) * w_stage, p.packed + (size_t)(k * KB + kb) * w_stage,
+                                 w_stage, afull_bar(sw));
+                    }
+                  }
+              }
             }
             __syncwarp();
           }
@@ -1036,9 +1109,9 @@ static int plan_launch(wsis::umma::Params &p, int K, int Cin, int Cout, int NS, 
     if (us_ == 3) us_ = 2;
     const int na = pool / us_;
     for (auto &c : pref) {
-      const int64_t misc = 1024 /*align*/ + 2 * p.KB * cpu * 4 + (2 * na + 2 * c[0] + 2 * c[1] + 5 + 2 * kUlSlots) * 8 + 64 +
+      const int64_t misc = 1024 /*align*/ + 2 * p.KB * cpu * 4 + (2 * na + 3 * c[0] + 2 * c[1] + 5 + 2 * kUlSlots) * 8 + 64 +
                            kUlSlots * kUlBytes;
-      smem = misc + (p.resident ? w_all : (int64_t)pool * w_stage) + c[0] * (int64_t)kRcBuf + c[1] * rec_buf;
+      smem = misc + (p.resident ? w_all : (int64_t)pool * 2 * w_stage) + c[0] * (int64_t)kRcBuf + c[1] * rec_buf;
       if (smem <= budget) {
         p.us = us_;
         p.lna = na == 8 ? 3 : na == 4 ? 2 : na == 2 ? 1 : 0;

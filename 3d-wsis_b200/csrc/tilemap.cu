@@ -44,10 +44,15 @@ __global__ void iota_kernel(int32_t *order, int64_t N, int64_t n_pad) {
 // Tile records: what one conv CTA needs to know about one tile of 128 destination rows.
 //   record (records + t * rec_stride_bytes(K), all of it meaningful)
 //     [0, 16K)                 valid[K][4]  u32   bit r of valid[k] = tile slot r has a source row through offset k
-//     [16K, 16K + 48)          nU u32 | amask u32 | P u32 | nact u32 | klist u8[32]: the nact active offsets, ascending
-//     [16K + 48, 16K+48+256K)  loc[K][128]  u16   row i < nact belongs to offset klist[i]: index of slot r's source row
-//                                                 through that offset in the tile's list of DISTINCT source rows
-//                                                 (0xFFFF where the slot has none); rows >= nact are unused
+//     [16K, 16K + 80)          nU u32 | amask u32 | P u32 | npack u32 | members u16[32]
+//                              A PACK is one or two active offsets whose valid-slot sets are disjoint (greedy first
+//                              fit in ascending offset order): members[i] = k0 | k1 << 8 (0xFF = none).  The conv
+//                              kernel assembles ONE operand block per pack (every slot takes the row of whichever
+//                              member it has a neighbour through) and multiplies it once per member with that
+//                              member's lane mask and weights: a surface tile has 27 active offsets but ~16 packs.
+//     [16K + 80, ...+256K)     loc[K][128]  u16   row i < npack: index of slot r's source row, through the pack's
+//                                                 member that reaches it, in the tile's list of DISTINCT source rows
+//                                                 (0xFFFF where the slot has none); rows >= npack are unused
 //   unique rows (uidx + t * 128K)  i32[nU]        the distinct source rows the tile reads; a surface patch of 128
 //                                                 voxels reads ~160-230 distinct rows through ~480-1400 entries, so the
 //                                                 conv kernel fetches (and converts) every source row ONCE per tile
@@ -70,7 +75,9 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
   int32_t *s_first = s_tab + HT;                                        // [HT] first entry (k * 128 + slot) of the row
   uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_first + HT);        // [4 K] bitmap of first entries
   int32_t *s_pre = reinterpret_cast<int32_t *>(s_bits + 4 * K);         // [4 K + 1] exclusive prefix of its popcounts
-  uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_pre + 4 * K + 4);    // [K][128] table slot of each entry
+  uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_pre + 4 * K + 4);     // [4 K] valid-slot masks of the offsets
+  int32_t *s_packof = reinterpret_cast<int32_t *>(s_vm + 4 * K);        // [K] pack of each offset, [K] = npack
+  uint16_t *s_pos = reinterpret_cast<uint16_t *>(s_packof + K + 4);     // [K][128] table slot of each entry
   const int64_t t = blockIdx.x;
   const int r = threadIdx.x, lane = r & 31, w = r >> 5;
   const int32_t dst = __ldg(order + t * kTile + r);
@@ -92,6 +99,7 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
     const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
     if (lane == 0) {
       valid[k * 4 + w] = bal;
+      s_vm[k * 4 + w] = bal;
       if (bal) atomicAdd(s_cnt + k, __popc(bal));
     }
     if (v >= 0) {
@@ -130,28 +138,46 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
       run += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) s_pre[4 * K] = run;
+  } else if (w == 1) {
+    // packs: lane i keeps pack i (mask of occupied slots, member count, members); offsets are placed first fit
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, cnt = 0, mem = 0xFFFFu;
+    int npack = 0;
+    for (int k = 0; k < K; ++k) {
+      const uint32_t v0 = s_vm[4 * k], v1 = s_vm[4 * k + 1], v2 = s_vm[4 * k + 2], v3 = s_vm[4 * k + 3];
+      if ((v0 | v1 | v2 | v3) == 0) {
+        if (lane == 0) s_packof[k] = -1;
+        continue;
+      }
+      const bool fit = lane < npack && cnt < 2 && (((m0 & v0) | (m1 & v1) | (m2 & v2) | (m3 & v3)) == 0);
+      const uint32_t bal = __ballot_sync(0xffffffffu, fit);
+      const int tgt = bal ? __ffs(bal) - 1 : npack;
+      if (!bal) ++npack;
+      if (lane == tgt) {
+        m0 |= v0, m1 |= v1, m2 |= v2, m3 |= v3;
+        mem = cnt == 0 ? (0xFF00u | (uint32_t)k) : ((mem & 0xFFu) | ((uint32_t)k << 8));
+        ++cnt;
+      }
+      if (lane == 0) s_packof[k] = tgt;
+    }
+    if (npack == 0) npack = 1;  // a tile without any entry still sends one all-lanes-off unit through the pipeline
+    reinterpret_cast<uint16_t *>(rec + 16 * K + 16)[lane] = lane < npack ? (uint16_t)mem : (uint16_t)0xFFFFu;
+    if (lane == 0) s_packof[K] = npack;
   }
   __syncthreads();
   const int nU = s_pre[4 * K];
-  uint32_t amask = 0;  // offsets with at least one entry (every thread computes it: K <= 32 counters)
-  for (int k = 0; k < K; ++k)
-    if (s_cnt[k] > 0) amask |= 1u << k;
+  const int npack = s_packof[K];
   int32_t *u = uidx + t * (int64_t)(kTile * K);
   uint16_t *loc = reinterpret_cast<uint16_t *>(rec + rec_hdr_bytes(K));
+  for (int i = 0; i < npack; ++i) loc[i * kTile + r] = 0xFFFFu;
   for (int k = 0; k < K; ++k) {
     const int32_t v = s_map[k * kTile + r];
-    uint16_t l = 0xFFFFu;
     if (v >= 0) {
       const int key = s_first[s_pos[k * kTile + r]];  // first entry of this row
       const int rank = s_pre[key >> 5] + __popc(s_bits[key >> 5] & ((1u << (key & 31)) - 1u));
-      l = (uint16_t)rank;
       if (key == k * kTile + r) u[rank] = v;
+      loc[s_packof[k] * kTile + r] = (uint16_t)rank;  // the members of a pack reach disjoint slots
     }
-    // loc rows are stored compacted over the ACTIVE offsets (row = rank of k in amask): the conv builders walk them
-    // by rank without a lookup; a tile without any entry keeps one all-0xFFFF row (its dummy unit)
-    if ((amask >> k) & 1u) loc[__popc(amask & ((1u << k) - 1u)) * kTile + r] = l;
   }
-  if (amask == 0) loc[r] = 0xFFFFu;
   if (r == 0) {
     uint32_t am = 0;
     int P = 0;
@@ -159,13 +185,9 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
       if (s_cnt[k] > 0) am |= 1u << k;
       P += s_cnt[k];
     }
-    if (am == 0) am = 1u;  // a tile without any entry still sends one all-lanes-off unit through the pipeline
-    *reinterpret_cast<uint4 *>(rec + 16 * K) = make_uint4((uint32_t)nU, am, (uint32_t)P, (uint32_t)__popc(am));
-    uint8_t *klist = rec + 16 * K + 16;
-    int n = 0;
-    for (uint32_t mm = am; mm; mm &= mm - 1) klist[n++] = (uint8_t)(__ffs(mm) - 1);
-    for (; n < 32; ++n) klist[n] = 0;
-    meta[t] = make_int4(rec_stride_bytes(K), nU, (int)am, P);
+    if (am == 0) am = 1u;
+    *reinterpret_cast<uint4 *>(rec + 16 * K) = make_uint4((uint32_t)nU, am, (uint32_t)P, (uint32_t)npack);
+    meta[t] = make_int4(rec_stride_bytes(K), nU, npack, P);
     atomicMax(stats, P);  // most entries / most distinct rows of a tile of the map
     atomicMax(stats + 1, nU);
   }
@@ -249,7 +271,8 @@ int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const
                reinterpret_cast<uintptr_t>(meta)) & 15) == 0,
              "tile_records: records/uidx/meta must be 16-byte aligned");
   const int HT = tile_table_slots(K);
-  size_t smem = ((size_t)K * kTile + K + 8 + 2 * HT + 8 * K + 8) * sizeof(int32_t) + (size_t)K * kTile * sizeof(uint16_t);
+  size_t smem = ((size_t)K * kTile + K + 8 + 2 * HT + 8 * K + 8 + 4 * K + K + 4) * sizeof(int32_t) +
+                (size_t)K * kTile * sizeof(uint16_t);
   // the opt-in is per device: set it on every call rather than caching it process-wide (multi-GPU processes)
   WSIS_CUDA(cudaFuncSetAttribute(tile_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tile_record_kernel<<<(unsigned)n_tiles, kTile, smem, as_stream(stream)>>>(

@@ -10,7 +10,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
-LIB_PATH = os.path.join(_HERE, "libwsis_b200.so")
+LIB_PATH = os.environ.get("WSIS_B200_LIB") or os.path.join(_HERE, "libwsis_b200.so")  # override: experiment builds
 HEADER_PATH = os.path.join(_ROOT, "include", "wsis_b200.h")
 
 _SCALARS = {

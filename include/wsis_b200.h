@@ -121,13 +121,15 @@ int wsis_conv_simt(const float *src, const int32_t *map, int64_t n_dst, int K, i
  * wsis_identity_order gives the trivial order for callers without coordinates.
  * wsis_tile_records turns a neighbour map into per-tile RECORDS, the only form of the rulebook the tensor-core
  * kernel reads: for tile t (destination rows order[128t .. 128t+127]) and `m[r,k] = map[order[..], flip ? K-1-k : k]`
- *   records + t * wsis_tile_record_stride(K)   (stride = 16 K + 48 + 256 K bytes):
- *     valid[K][4] u32 | {nU u32, amask u32, P u32, nact u32, klist u8[32]} | loc[K][128] u16
- *     valid[k] = tile slots that have a source row through offset k; loc[k][r] = index of slot r's source row in the
- *     tile's list of DISTINCT source rows (0xFFFF where the slot has none); amask = offsets with at least one entry
- *     (1 if the tile has none at all), klist = those nact offsets in ascending order; P = entries of the tile
+ *   records + t * wsis_tile_record_stride(K)   (stride = 16 K + 80 + 256 K bytes):
+ *     valid[K][4] u32 | {nU u32, amask u32, P u32, npack u32, members u16[32]} | loc[K][128] u16
+ *     valid[k] = tile slots that have a source row through offset k; amask = offsets with at least one entry (1 if the
+ *     tile has none at all); P = entries of the tile.  A PACK is one or two active offsets with disjoint valid-slot
+ *     sets (greedy first fit in ascending offset order): members[i] = k0 | k1 << 8 (0xFF = none) for i < npack.
+ *     loc row i < npack: loc[i][r] = index, in the tile's list of DISTINCT source rows, of the row slot r reads through
+ *     the member of pack i that reaches it (0xFFFF where neither does)
  *   uidx + t * wsis_tile_unique_stride(K): int32[nU] the distinct source rows of the tile (any order)
- *   meta[t] = int32[4] {record bytes, nU, amask, P}
+ *   meta[t] = int32[4] {record bytes, nU, npack, P}
  *   stats = int32[2] {largest P, largest nU} over the tiles
  * records: uint8[num_tiles * stride], uidx: int32[num_tiles * unique_stride], meta: int32[num_tiles * 4], all 16-byte
  * aligned.  K <= 32. */

@@ -577,26 +577,38 @@ def _decode_records(t, K):
     rec = t.records.cpu().numpy()
     meta = t.meta.cpu().numpy()
     uidx = t.uidx.cpu().numpy()
-    assert t.stride == 16 * K + 48 + 256 * K
+    assert t.stride == 16 * K + 80 + 256 * K
     out = np.full((t.num_tiles * 128, K), -1, np.int32)
     for ti in range(t.num_tiles):
         r = rec[ti * t.stride:(ti + 1) * t.stride]
         valid = r[:16 * K].view(np.uint32).reshape(K, 4)
         hdr = r[16 * K:16 * K + 16].view(np.uint32)
-        nU, amask, P, nact = int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[3])
-        klist = r[16 * K + 16:16 * K + 48]
-        assert [int(k) for k in klist[:nact]] == [k for k in range(K) if amask >> k & 1] and nact == bin(amask).count("1")
-        locr = r[16 * K + 48:].view(np.uint16).reshape(K, 128).astype(np.int64)   # rows in klist (rank) order
-        loc = np.full((K, 128), 0xFFFF, np.int64)
-        for i in range(nact):
-            loc[int(klist[i])] = locr[i]
+        nU, amask, P, npack = int(hdr[0]), int(hdr[1]), int(hdr[2]), int(hdr[3])
+        members = r[16 * K + 16:16 * K + 80].view(np.uint16)
+        locr = r[16 * K + 80:].view(np.uint16).reshape(K, 128).astype(np.int64)   # one row per pack
         bits = np.unpackbits(valid.view(np.uint8).reshape(K, 16), axis=1, bitorder="little").astype(bool)
         assert P == bits.sum() and amask == (sum(1 << k for k in range(K) if bits[k].any()) or 1)
-        assert list(meta[ti]) == [t.stride, nU, amask, P]
+        assert list(meta[ti]) == [t.stride, nU, npack, P]
+        # packs: every active offset is a member of exactly one pack, at most two per pack, disjoint valid slots
+        seen = []
+        loc = np.full((K, 128), 0xFFFF, np.int64)
+        assert 1 <= npack <= max(1, int(bits.any(1).sum())) and np.all(members[npack:] == 0xFFFF)
+        for i in range(npack):
+            ks = [k for k in (int(members[i]) & 0xFF, int(members[i]) >> 8) if k != 0xFF]
+            assert (len(ks) >= 1 or P == 0) and all(bits[k].any() for k in ks)
+            if len(ks) == 2:
+                assert not (bits[ks[0]] & bits[ks[1]]).any()
+            seen += ks
+            for k in ks:
+                loc[k, bits[k]] = locr[i, bits[k]]
+            union = np.zeros(128, bool)
+            for k in ks:
+                union |= bits[k]
+            assert np.all(locr[i, ~union] == 0xFFFF)
+        assert sorted(seen) == [k for k in range(K) if bits[k].any()]
         uniq = uidx[ti * t.ustride:ti * t.ustride + nU]
         assert len(np.unique(uniq)) == nU                      # the tile's source rows, each exactly once
         assert P == 0 or (loc[bits].max() < nU and len(np.unique(loc[bits])) == nU)
-        assert np.all(loc[~bits] == 0xFFFF)
         for k in range(K):
             sl = np.nonzero(bits[k])[0]
             out[ti * 128 + sl, k] = uniq[loc[k, sl]]

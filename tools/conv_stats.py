@@ -60,7 +60,7 @@ def main():
     st = raw[:23 * 8].reshape(23, 8)
     tiles_cta0 = -(-tiles.num_tiles // 148)
     meta = tiles.meta.cpu().numpy()
-    units = int(sum(bin(int(m) & 0xffffffff).count("1") for m in meta[0::148, 2])) * (-(-cin // (32 if args.precision == "fp32" else 64)))
+    units = int(sum(int(m) for m in meta[0::148, 2])) * (-(-cin // (32 if args.precision == "fp32" else 64)))
     out = {"shape": args.shape, "level": args.level, "precision": args.precision, "tiles_cta0": tiles_cta0,
            "units_cta0": units, "roles": []}
     for wi, (name, waits) in enumerate(ROLES):
