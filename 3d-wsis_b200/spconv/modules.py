@@ -17,8 +17,22 @@ from wsis_b200 import ops as wsis_ops
 
 
 class SparseModule(nn.Module):
-    """Marker base class: subclasses receive a SparseConvTensor inside SparseSequential."""
-    pass
+    """Marker base class: subclasses receive a SparseConvTensor inside SparseSequential.
+
+    Derived parameter images (packed conv weights, folded BatchNorm) are invalidated whenever parameters are
+    (re)loaded, moved or converted, or the train/eval mode changes (wsis_b200.ops.invalidate_caches)."""
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        wsis_ops.invalidate_caches()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        wsis_ops.invalidate_caches()
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode=True):
+        wsis_ops.invalidate_caches()
+        return super().train(mode)
 
 
 def is_spconv_module(module):
@@ -28,7 +42,7 @@ def is_spconv_module(module):
 def _fold_bn(bn):
     """Eval-mode BatchNorm1d as (scale, shift); cached on the module per parameter version."""
     key = (bn.weight._version if bn.weight is not None else -1, bn.bias._version if bn.bias is not None else -1,
-           bn.running_mean._version, bn.running_var._version, bn.running_mean.data_ptr())
+           bn.running_mean._version, bn.running_var._version, bn.running_mean.data_ptr(), wsis_ops.cache_epoch())
     cache = getattr(bn, "_wsis_fold", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():

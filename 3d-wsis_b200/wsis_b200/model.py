@@ -11,6 +11,7 @@ reference `state_dict` loads with strict=True and fixed-seed initialisation is i
     GraphNetwork (ECC-GRU)  modules/model/graphnet.py:21-114, spg_modules.py:128-253
     Network                 modules/model/backbone_3D_WSIS.py:25-255
 """
+import ast
 import functools
 from collections import OrderedDict
 
@@ -236,7 +237,8 @@ class RNNGraphConvModule(nn.Module):
                 and isinstance(cell, GRUCellEx) and cell._ingate and cell.bias):
             # inference: one kernel per GRU step (message, gates, layer norms and the concatenation fused;
             # csrc/ecc.cu) instead of ~20 torch launches
-            key = tuple(p._version for p in cell.parameters()) + tuple(p.data_ptr() for p in cell.parameters())
+            key = tuple(p._version for p in cell.parameters()) + tuple(p.data_ptr() for p in cell.parameters()) + \
+                (W.cache_epoch(),)
             if getattr(self, "_packed_key", None) != key:
                 self._packed_key, self._packed = key, W.pack_ecc_gru(cell)
             tseg = W.SegmentIndex(edge_index[1], hx.shape[0])
@@ -338,12 +340,27 @@ class Network(nn.Module):
         self.w_ks = nn.Linear(d, d, bias=False)
         self.w_vs = nn.Linear(d, d, bias=False)
         self.feature_term = _head(norm_fn, d, 7)
+        # frozen sub-modules (backbone_3D_WSIS.py:35,131-136): eval() + requires_grad=False at construction and eval()
+        # again on every forward (:172-173)
+        fm = getattr(param, "fix_module", "[]")
+        self.fix_module = ast.literal_eval(fm) if isinstance(fm, str) else list(fm or [])
+        for name in self.fix_module:
+            module = getattr(self, name)
+            module.eval()
+            for prm in module.parameters():
+                prm.requires_grad = False
+
+    def load_state_dict(self, *args, **kwargs):
+        W.invalidate_caches()   # derived parameter images (packed weights, folded BN) are rebuilt at the next forward
+        return super().load_state_dict(*args, **kwargs)
 
     def forward(self, input, input_map, extra_data):
         """Same inputs and the same result dict as backbone_3D_WSIS.py:164-255.  Optional extra_data keys that
         avoid host syncs / rebuilds: "sp_index" (ops.SegmentIndex of `superpoint`), "edge_index_u" (SegmentIndex of
         edge_u_list), "num_superpoints"."""
         ret = {}
+        for name in self.fix_module:
+            getattr(self, name).eval()
         output = self.output_layer(self.unet(self.input_conv(input)))
         if extra_data.get("keep_unet_features"):      # parity checks compare the U-Net output itself
             extra_data["unet_features"] = output.features

@@ -61,6 +61,24 @@ def _bytes(n, device):
     return torch.empty(max(int(n), 16), dtype=torch.uint8, device=device)
 
 
+# Derived device-side images of parameters (pre-swizzled conv weights, folded BatchNorm scale/shift, packed ECC-GRU
+# matrices) are cached per parameter (data_ptr, tensor._version).  In-place edits through `.data`
+# (`w.data.copy_()`, `bn.weight.data.fill_()`: backbone_3D_WSIS.py:156-157 set_bn_init, spconv test_conv.py:360-361)
+# do NOT bump `_version`, so the caches also carry this epoch: it is bumped by load_state_dict / .to() / .train() of
+# the spconv modules and of the mirror Network, and callers that mutate `.data` after the first forward must call
+# invalidate_caches() themselves (documented in INTEGRATION.md).
+_CACHE_EPOCH = 0
+
+
+def invalidate_caches():
+    global _CACHE_EPOCH
+    _CACHE_EPOCH += 1
+
+
+def cache_epoch():
+    return _CACHE_EPOCH
+
+
 def launch_count():
     return int(lib().value("wsis_launch_count"))
 
@@ -162,7 +180,9 @@ class Rulebook:
 
     # (map, flip) for: y[dst] = sum_k x[map[dst,k]] W[k]
     def fwd_map(self):
-        return (self.nbr_in, 1) if self.kind == "subm" else (self.nbr_out, 0)
+        # submanifold rulebooks of ODD kernels without dilation are symmetric (nbr_out[o,k] == nbr_in[o,K-1-k]); any
+        # other submanifold rulebook carries its own output-side map (rulebook_subm builds it)
+        return (self.nbr_in, 1) if (self.kind == "subm" and self.nbr_out is None) else (self.nbr_out, 0)
 
     def bwd_map(self):  # maps rows of the conv INPUT side to rows of the OUTPUT side
         return (self.nbr_in, 0)
@@ -204,7 +224,17 @@ def rulebook_subm(indices, spatial_shape, ksize=3, dilation=1, batch_size=None):
         vals = torch.empty((slots,), dtype=torch.int32, device=dev)
         lib().call("wsis_rulebook_subm", _ptr(indices), N, _c3(ks), _c3(dil), _c3(shape), _ptr(keys), _ptr(vals), slots,
                    _ptr(nbr), _stream())
-    return Rulebook("subm", K, N, N, nbr, None, indices, indices, shape, shape, _batch_of(batch_size))
+    rb = Rulebook("subm", K, N, N, nbr, None, indices, indices, shape, shape, _batch_of(batch_size))
+    if any(k % 2 == 0 for k in ks) or any(d != 1 for d in dil):
+        # Like the reference (spconv_ops.h:74-77) the submanifold padding is ks/2 whatever the dilation, so for even
+        # kernels or dilation > 1 the pair (k, i -> o) has no mirror image (K-1-k, o -> i): the forward / wgrad map
+        # cannot be read off nbr_in by flipping the offset.  Build the output-side map from the pairs themselves.
+        pairs, num = rb.pairs()
+        nbr_out = torch.full((N, K), -1, dtype=torch.int32, device=dev)
+        if N > 0:
+            lib().call("wsis_nbr_from_pairs", _ptr(pairs), _ptr(num), pairs.shape[2], K, 1, _ptr(nbr_out), _stream())
+        rb.nbr_out = nbr_out
+    return rb
 
 
 def _batch_of(batch_size):
@@ -286,7 +316,7 @@ class PackedWeights:
 
     def get(self, weight3, transpose_w, precision):
         Cin, Cout = (weight3.shape[2], weight3.shape[1]) if transpose_w else (weight3.shape[1], weight3.shape[2])
-        key = (weight3.data_ptr(), weight3._version, tuple(weight3.shape), transpose_w, precision)
+        key = (weight3.data_ptr(), weight3._version, tuple(weight3.shape), transpose_w, precision, _CACHE_EPOCH)
         if key != self.key:
             K = weight3.shape[0]
             nbytes = lib().value("wsis_conv_pack_bytes", K, Cin, Cout, precision)

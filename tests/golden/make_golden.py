@@ -7,7 +7,7 @@ spg_modules.py) on top of the reference's own spconv Python package and its CPU 
 (oracle/Makefile).  What is NOT in the reference tree or not installed here is stubbed with the restatements
 the SURVEY names (§8c) -- these pieces are "parity unpinned":
     torch_scatter.scatter      -> index_add_/amax formulation
-    torch_geometric NNConv     -> MessagePassing stub (flow target_to_source, aggr mean)
+    torch_geometric NNConv     -> MessagePassing stub (flow source_to_target -- spg_modules.py:68 never forwards `flow` -- aggr mean)
     pointgroup_ops             -> oracle.voxelization_idx / voxelization
     ecc.GraphConvInfo (igraph) -> tensor-only stand-in with the same get_buffers()/get_pyg_buffers()
     func_helper, utils, ecc    -> empty modules (imported by the reference, unused on this path)

@@ -247,6 +247,23 @@ def test_oracle_random_walk_properties(orc):
     assert set(np.nonzero(final0 != -100)[0].tolist()) == {4, 6, 39, 41}   # one hop from each seed
 
 
+def test_oracle_random_walk_matches_reference_golden(orc, golden_dir):
+    """The oracle's restatement against the reference's OWN `weak_label_propagation`
+    (modules/datasets/scannetv2_dataset.py:664-735, cut out with ast and executed by tests/golden/make_golden_rw.py)
+    on a 150k-point scene's superpoint graph (S = 3138, 16 288 directed edges), iterations_num 0, 1 and 3: pseudo labels
+    identical, scores bit-equal (both are numpy float64 doing the same operations in the same order)."""
+    g = np.load(os.path.join(golden_dir, "rw_scene0.npz"))
+    S, e = int(g["S"]), g["edges"].astype(np.int64)
+    adj = np.zeros((S, S))
+    adj[e[:, 0], e[:, 1]] = 1
+    A = orc.dense_affinity(e[:, 0], e[:, 1], g["aff"], S)
+    for it in (0, 1, 3):
+        final, score = orc.weak_label_propagation(g["seed_label"].astype(np.int64), adj, g["conf"], g["pred"].astype(np.int64), A, it)
+        assert np.array_equal(final.astype(np.int32), g["pseudo_it%d" % it])
+        assert np.array_equal(score, g["score_it%d" % it])
+        assert (final != -100).sum() > (10, 20, 0, 40)[it]
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the C-ABI library: loads, exports every declared symbol, pure helpers answer without a GPU
 # ---------------------------------------------------------------------------------------------------------
@@ -356,6 +373,23 @@ def test_spconv_api_surface():
     out = seq(t)                                                    # dense modules act on .features in place
     assert out is t and tuple(t.features.shape) == (3, 4)
     assert spconv.ops.get_conv_output_size([19, 18, 17], [2] * 3, [2] * 3, [0] * 3, [1] * 3) == [9, 9, 8]
+
+
+def test_reference_model_files_run_on_the_dropin():
+    """The boundary claim of DESIGN.md 1 / INTEGRATION.md 1: the reference's own model files
+    (modules/model/backbone_3D_WSIS.py, sparse_unet3d.py, graphnet.py, spg_modules.py), imported unmodified, build
+    their Network on THIS repository's `spconv` package and end up with exactly the mirror's state_dict (same keys
+    in the same order, bit-equal tensors under the same seed).  Needs the reference tree (this container only)."""
+    import json
+    ref = os.environ.get("WSIS_REFERENCE", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "modules/model/backbone_3D_WSIS.py")):
+        pytest.skip("reference tree not present on this box")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_dropin_check.py")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["same_keys"] and res["n_keys"] > 300 and res["different_tensors"] == []
+    assert res["uses_dropin"] and res["ublock_is_reference"] and res["sparse_conv_modules"] == 49
 
 
 def test_network_parameters_match_reference_golden(golden_dir):

@@ -202,6 +202,36 @@ def test_subm_conv_forward(W, orc, cin, cout, prec, tol):
     assert rel(out.cpu().numpy(), ref) < tol
 
 
+@pytest.mark.parametrize("ksize,dil", [(3, 2), (2, 1), (4, 1), (3, 3)])
+def test_subm_conv_dilated_and_even_kernels(W, orc, ksize, dil):
+    """Submanifold rulebooks with dilation > 1 or an even kernel are NOT symmetric (the padding is ks/2 whatever the
+    dilation, spconv_ops.h:74-77), so the forward / wgrad map cannot be the flipped input-side map: the module path
+    (SubMConv3d forward, din and dW through autograd) is checked against the oracle on those shapes."""
+    import spconv
+    rng = np.random.default_rng(100 * ksize + dil)
+    shape = [19, 18, 17]
+    c = gen_coords(rng, shape, 1200, 2)
+    cin, cout, K = 32, 32, ksize ** 3
+    f = rng.uniform(-1, 1, (len(c), cin)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (ksize, ksize, ksize, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    g = rng.uniform(-1, 1, (len(c), cout)).astype(np.float32)
+    pairs, num = orc.rulebook_subm(c, 2, shape, ksize, dil)
+    ref = orc.indice_conv(f, w.reshape(K, cin, cout), pairs, num, len(c))
+    din_ref, dw_ref = orc.indice_conv_backward(f, w.reshape(K, cin, cout), g, pairs, num)
+    conv = spconv.SubMConv3d(cin, cout, ksize, padding=ksize // 2, dilation=dil, bias=False, indice_key="k").cuda()
+    with torch.no_grad():
+        conv.weight.copy_(cu(w))
+    x = cu(f).requires_grad_(True)
+    out = conv(spconv.SparseConvTensor(x, cu(c), shape, 2)).features
+    assert rel(out.detach().cpu().numpy(), ref) < FP32_TOL
+    out.backward(cu(g))
+    assert rel(x.grad.cpu().numpy(), din_ref) < FP32_TOL
+    assert rel(conv.weight.grad.cpu().numpy().reshape(K, cin, cout), dw_ref) < FP32_TOL
+    with torch.no_grad():                                   # the fused inference path uses the same maps
+        out2 = conv(spconv.SparseConvTensor(cu(f), cu(c), shape, 2)).features
+    assert rel(out2.cpu().numpy(), ref) < FP32_TOL
+
+
 @pytest.mark.parametrize("prec,tol", [("simt", 2e-6), ("fp32", FP32_TOL), ("bf16", BF16_TOL)])
 def test_conv_fused_prologue_and_residual(W, orc, prec, tol):
     rng = np.random.default_rng(5)
@@ -435,6 +465,18 @@ def test_random_walk_matches_reference_numpy(W, orc, iterations):
     assert (final_ref != -100).sum() > 0
 
 
+@pytest.mark.parametrize("iterations", [0, 1, 3])
+def test_random_walk_matches_reference_golden(W, golden_dir, iterations):
+    """The device random walk against outputs of the reference's OWN method (scannetv2_dataset.py:664-735 executed by
+    tests/golden/make_golden_rw.py) on a full scene's superpoint graph: labels identical, scores to 1e-12."""
+    g = np.load(os.path.join(golden_dir, "rw_scene0.npz"))
+    e = g["edges"].astype(np.int64)
+    pseudo, score = W.random_walk(cu(e[:, 0]), cu(e[:, 1]), cu(g["aff"]), cu(g["seed_label"].astype(np.int64)),
+                                  cu(g["pred"].astype(np.int64)), cu(g["conf"]), 20, iterations)
+    assert np.array_equal(pseudo.cpu().numpy().astype(np.int32), g["pseudo_it%d" % iterations])
+    assert np.abs(score.cpu().numpy() - g["score_it%d" % iterations]).max() < 1e-12
+
+
 # ---------------------------------------------------------------------------------------------------------
 # end to end against the reference's own outputs (tests/golden/make_golden.py)
 # ---------------------------------------------------------------------------------------------------------
@@ -507,6 +549,42 @@ def test_drop_in_module_api_unfused_equals_fused(W):
         x.features = torch.relu(seq[0](x.features))
         plain = seq[2](x).features
     assert float((fused - plain).abs().max()) < FP32_TOL * float(plain.abs().max())
+
+
+def test_public_api_train_mode_autograd(W, orc):
+    """A SparseSequential(BatchNorm1d, ReLU, SubMConv3d) built only through the public names of the drop-in, in TRAIN
+    mode with autograd (batch statistics, no fusion): forward and the gradients of the input and of every parameter
+    against torch BatchNorm + the oracle's conv forward / backward (spconv_ops.h:253-433)."""
+    import spconv
+    rng = np.random.default_rng(77)
+    shape = [19, 18, 17]
+    c = gen_coords(rng, shape, 1500, 2)
+    cin, cout = 32, 64
+    f = rng.uniform(-1, 1, (len(c), cin)).astype(np.float32)
+    g = rng.uniform(-1, 1, (len(c), cout)).astype(np.float32)
+    torch.manual_seed(3)
+    seq = spconv.SparseSequential(torch.nn.BatchNorm1d(cin, eps=1e-4, momentum=0.1), torch.nn.ReLU(),
+                                  spconv.SubMConv3d(cin, cout, 3, padding=1, bias=False, indice_key="k")).cuda().train()
+    x = cu(f).requires_grad_(True)
+    out = seq(spconv.SparseConvTensor(x, cu(c), shape, 2)).features
+    out.backward(cu(g))
+    # reference formulation on the host: torch BN (train) + ReLU, then the oracle's indice_conv / backward
+    xr = torch.from_numpy(f).requires_grad_(True)
+    bn = torch.nn.BatchNorm1d(cin, eps=1e-4, momentum=0.1).train()
+    with torch.no_grad():
+        bn.weight.copy_(seq[0].weight.detach().cpu())
+        bn.bias.copy_(seq[0].bias.detach().cpu())
+    a = torch.relu(bn(xr))
+    w = seq[2].weight.detach().cpu().numpy().reshape(27, cin, cout)
+    pairs, num = orc.rulebook_subm(c, 2, shape, 3, 1)
+    ref = orc.indice_conv(a.detach().numpy(), w, pairs, num, len(c))
+    da, dw = orc.indice_conv_backward(a.detach().numpy(), w, g, pairs, num)
+    a.backward(torch.from_numpy(da))
+    assert rel(out.detach().cpu().numpy(), ref) < FP32_TOL
+    assert rel(seq[2].weight.grad.cpu().numpy().reshape(27, cin, cout), dw) < FP32_TOL
+    assert rel(x.grad.cpu().numpy(), xr.grad.numpy()) < 2e-4
+    assert rel(seq[0].weight.grad.cpu().numpy(), bn.weight.grad.numpy()) < 2e-4
+    assert rel(seq[0].running_mean.cpu().numpy(), bn.running_mean.numpy()) < 1e-5
 
 
 # ---------------------------------------------------------------------------------------------------------
