@@ -1,0 +1,270 @@
+// Training-step kernels around the sparse convs (BASELINE.json configs[2]; reference: train_scannetv2.py:200-252,
+// 734-738): batch-statistics BatchNorm whose normalisation rides in the conv's gather prologue (only the column
+// reductions and the backward elementwise pass are separate kernels), and one AdamW launch over the flat parameter
+// buffer with the ECC gradient clamp (train_scannetv2.py:246-249) and the 1/world gradient average folded in.
+//
+// BatchNorm1d (train) over x f32[N, C] (the reference: torch.nn.BatchNorm1d / SyncBatchNorm, sparse_unet3d.py:135-171):
+//   forward   sums[c] = (sum x, sum x^2), count          -> [all-reduce across ranks when the statistics are synced]
+//             finalize: mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, running stats
+//             y = relu(x*scale + shift) is NOT materialised: the next conv applies it while gathering rows
+//   backward  da = gradient w.r.t. y (the conv's dgrad);  dy = da * [x*scale+shift > 0]
+//             sums[c] = (sum dy, sum dy*xhat)            -> [all-reduce]
+//             dx = scale * (dy - mean(dy) - xhat * mean(dy*xhat)),  dgamma = sum dy*xhat (local), dbeta = sum dy (local)
+// All reductions are two-stage with a fixed order (block partials in fp32, combined in fp64): deterministic.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace wsis {
+
+constexpr int kBnThreads = 256;
+
+// mode 0: (x, x^2); mode 1: (dy, dy*xhat) with dy = da * relu-mask
+template <int MODE>
+__global__ void __launch_bounds__(kBnThreads)
+bn_colsum_kernel(const float *__restrict__ x, const float *__restrict__ da, int64_t N, int C,
+                 const float *__restrict__ stat /* mean | invstd | scale | shift, [4][C] */, int relu,
+                 float *__restrict__ partial /* [gridDim.x][2][C] */) {
+  extern __shared__ float sm[];  // [rows_per_pass][2][C]
+  const int tpr = (C + 3) / 4;                  // threads per row (4 channels each)
+  const int rpp = kBnThreads / tpr;             // rows per pass
+  const int tr = threadIdx.x / tpr, tq = threadIdx.x % tpr;
+  const int c0 = tq * 4;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  float mean[4], invstd[4], scale[4], shift[4];
+  const bool active = tr < rpp;
+  if (MODE == 1 && active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = min(c0 + j, C - 1);
+      mean[j] = stat[c], invstd[j] = stat[C + c], scale[j] = stat[2 * C + c], shift[j] = stat[3 * C + c];
+    }
+  }
+  const bool vec = (C % 4 == 0);
+  // MODE 0 accumulates around a per-block pivot (the block's first row) so that sum (x-p)^2 does not cancel in fp32
+  // when |mean| >> std; the combine kernel undoes the shift in fp64
+  float piv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (MODE == 0 && active) {
+    int64_t pr = (int64_t)blockIdx.x * rpp;
+    if (pr < N) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) piv[j] = c0 + j < C ? x[pr * C + c0 + j] : 0.f;
+    }
+  }
+  if (active) {
+    for (int64_t r = (int64_t)blockIdx.x * rpp + tr; r < N; r += (int64_t)gridDim.x * rpp) {
+      float xv[4], gv[4];
+      if (vec) {
+        float4 t = *reinterpret_cast<const float4 *>(x + r * C + c0);
+        xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w;
+        if (MODE == 1) {
+          float4 g = *reinterpret_cast<const float4 *>(da + r * C + c0);
+          gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xv[j] = c0 + j < C ? x[r * C + c0 + j] : 0.f;
+          if (MODE == 1) gv[j] = c0 + j < C ? da[r * C + c0 + j] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (MODE == 0) {
+          float d = xv[j] - piv[j];
+          s1[j] += d;
+          s2[j] = fmaf(d, d, s2[j]);
+        } else {
+          float dy = (relu && fmaf(xv[j], scale[j], shift[j]) <= 0.f) ? 0.f : gv[j];
+          s1[j] += dy;
+          s2[j] = fmaf(dy, (xv[j] - mean[j]) * invstd[j], s2[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j < C) {
+        sm[(tr * 2 + 0) * C + c0 + j] = s1[j];
+        sm[(tr * 2 + 1) * C + c0 + j] = s2[j];
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) {
+    float acc = 0.f;
+    for (int r = 0; r < rpp; ++r) acc += sm[r * 2 * C + i];
+    partial[(int64_t)blockIdx.x * 2 * C + i] = acc;
+  }
+}
+
+// sums[0..2C) = sum over blocks of the partials (fp64, fixed order: one warp per column, lanes stride over the blocks,
+// butterfly reduction); sums[2C] = count (forward only); the backward form also writes the LOCAL parameter gradients
+// dgamma = sum dy*xhat, dbeta = sum dy.
+// `x` != NULL (forward statistics): block b accumulated around the pivot p_b = x[b*rpp, c] over n_b rows, so
+//   sum x = sum_b (s1_b + n_b p_b),  sum x^2 = sum_b (s2_b + 2 p_b s1_b + n_b p_b^2).
+__global__ void __launch_bounds__(256)
+bn_combine_kernel(const float *__restrict__ partial, int nblocks, int C, double count, int write_count,
+                  double *__restrict__ sums, float *__restrict__ dgamma, float *__restrict__ dbeta,
+                  const float *__restrict__ x, int64_t N, int rpp) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // column of [sum1 | sum2]
+  if (i < 2 * C) {
+    const int c = i < C ? i : i - C;
+    double acc = 0.0;
+    for (int b = lane; b < nblocks; b += 32) {
+      if (x) {
+        int64_t r0 = (int64_t)b * rpp;
+        if (r0 >= N) continue;
+        double nb = 0.0;                       // rows r0 + j + k * nblocks * rpp < N, j < rpp
+        for (int j = 0; j < rpp && r0 + j < N; ++j) nb += (double)((N - (r0 + j) - 1) / ((int64_t)nblocks * rpp) + 1);
+        double p = (double)x[r0 * C + c];
+        double s1 = (double)partial[(int64_t)b * 2 * C + c], s2 = (double)partial[(int64_t)b * 2 * C + C + c];
+        acc += i < C ? s1 + nb * p : s2 + 2.0 * p * s1 + nb * p * p;
+      } else {
+        acc += (double)partial[(int64_t)b * 2 * C + i];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      sums[i] = acc;
+      if (dbeta && i < C) dbeta[i] = (float)acc;
+      if (dgamma && i >= C) dgamma[i - C] = (float)acc;
+    }
+  }
+  if (write_count && blockIdx.x == 0 && threadIdx.x == 0) sums[2 * C] = count;
+}
+
+__global__ void bn_finalize_kernel(const double *__restrict__ sums, int C, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float eps, float momentum,
+                                   float *__restrict__ running_mean, float *__restrict__ running_var,
+                                   float *__restrict__ stat) {
+  const double n = sums[2 * C];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double mean = sums[c] / n;
+    double var = sums[C + c] / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    float scale = g * invstd;
+    stat[c] = (float)mean;
+    stat[C + c] = invstd;
+    stat[2 * C + c] = scale;
+    stat[3 * C + c] = b - (float)mean * scale;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) {
+      double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ da, int64_t N, int C,
+                    const float *__restrict__ stat, int relu, const double *__restrict__ sums,
+                    const double *__restrict__ count, const float *__restrict__ extra, float *__restrict__ dx) {
+  const int64_t total = N * C;
+  const double n = *count;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float xv = x[i];
+    float scale = __ldg(stat + 2 * C + c);
+    float dy = (relu && fmaf(xv, scale, __ldg(stat + 3 * C + c)) <= 0.f) ? 0.f : da[i];
+    float xhat = (xv - __ldg(stat + c)) * __ldg(stat + C + c);
+    float m1 = (float)(sums[c] / n), m2 = (float)(sums[C + c] / n);
+    float v = scale * (dy - m1 - xhat * m2);
+    dx[i] = extra ? v + extra[i] : v;
+  }
+}
+
+// torch.optim.AdamW (decoupled weight decay, bias-corrected), one launch over the flat buffers.
+__global__ void __launch_bounds__(256)
+adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+             int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+             float grad_scale, int64_t clamp_begin, int64_t clamp_end) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    if (i >= clamp_begin && i < clamp_end) gi = fminf(fmaxf(gi, -1.f), 1.f);
+    float pi = p[i] * (1.f - lr * weight_decay);
+    float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+static int bn_grid(int64_t N, int C, int *rpp_out) {
+  int tpr = (C + 3) / 4;
+  int rpp = kBnThreads / tpr;
+  *rpp_out = rpp;
+  int64_t blocks = std::min<int64_t>(std::min<int64_t>(ceil_div(N, (int64_t)rpp * 4), (int64_t)sm_count() * 4), 1024);
+  return (int)std::max<int64_t>(blocks, 1);
+}
+
+}  // namespace wsis
+
+using namespace wsis;
+
+extern "C" {
+
+int64_t wsis_bn_ws_bytes(int64_t N, int C) {
+  int rpp;
+  return (int64_t)bn_grid(N, C, &rpp) * 2 * C * sizeof(float);
+}
+
+int wsis_bn_stats(const float *x, int64_t N, int C, void *ws, double *sums, wsis_stream_t stream) {
+  WSIS_CHECK(C >= 1 && C <= 1024, "bn_stats: 1 <= C <= 1024");
+  cudaStream_t st = as_stream(stream);
+  int rpp, blocks = bn_grid(N, C, &rpp);
+  bn_colsum_kernel<0><<<blocks, kBnThreads, sizeof(float) * rpp * 2 * C, st>>>(x, nullptr, N, C, nullptr, 0, (float *)ws);
+  WSIS_LAUNCH_OK();
+  bn_combine_kernel<<<(2 * C + 7) / 8, 256, 0, st>>>((const float *)ws, blocks, C, (double)N, 1, sums, nullptr, nullptr, x, N, rpp);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_bn_finalize(const double *sums, int C, const float *gamma, const float *beta, float eps, float momentum,
+                     float *running_mean, float *running_var, float *stat, wsis_stream_t stream) {
+  bn_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(sums, C, gamma, beta, eps, momentum, running_mean, running_var, stat);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_bn_bwd_reduce(const float *x, const float *da, int64_t N, int C, const float *stat, int relu, void *ws,
+                       double *sums, float *dgamma, float *dbeta, wsis_stream_t stream) {
+  WSIS_CHECK(C >= 1 && C <= 1024, "bn_bwd_reduce: 1 <= C <= 1024");
+  cudaStream_t st = as_stream(stream);
+  int rpp, blocks = bn_grid(N, C, &rpp);
+  bn_colsum_kernel<1><<<blocks, kBnThreads, sizeof(float) * rpp * 2 * C, st>>>(x, da, N, C, stat, relu, (float *)ws);
+  WSIS_LAUNCH_OK();
+  bn_combine_kernel<<<(2 * C + 7) / 8, 256, 0, st>>>((const float *)ws, blocks, C, 0.0, 0, sums, dgamma, dbeta, nullptr, 0, 0);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_bn_bwd_apply(const float *x, const float *da, int64_t N, int C, const float *stat, int relu,
+                      const double *sums, const double *count, const float *extra, float *dx, wsis_stream_t stream) {
+  if (N == 0) return 0;
+  int64_t total = N * C;
+  unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+  bn_bwd_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, da, N, C, stat, relu, sums, count, extra, dx);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_adamw_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int64_t step, float grad_scale, int64_t clamp_begin,
+                    int64_t clamp_end, wsis_stream_t stream) {
+  if (n == 0) return 0;
+  WSIS_CHECK(step >= 1, "adamw: step counts from 1");
+  float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)sm_count() * 8);
+  adamw_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt,
+                                                      grad_scale, clamp_begin, clamp_end);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

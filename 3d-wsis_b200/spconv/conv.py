@@ -69,7 +69,7 @@ class SparseConvolution(SparseModule):
             bound = 1 / math.sqrt(fan_in)
             init.uniform_(self.bias, -bound, bound)
 
-    def forward(self, input, _prologue=None, _residual=None):
+    def forward(self, input, _prologue=None, _residual=None, _bn_train=None):
         """`_prologue` = (scale, shift, relu) and `_residual` are the fusion hooks used by SparseSequential and by
         wsis_b200.model (inference only); plain calls behave exactly like the reference module."""
         assert isinstance(input, spconv.SparseConvTensor)
@@ -108,7 +108,18 @@ class SparseConvolution(SparseModule):
                     self.output_padding, self.subm, self.transposed, grid=input.grid)
                 input.indice_dict[self.indice_key] = (outids, indices, indice_pairs, indice_pair_num, spatial_shape)
         needs_grad = torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad)
-        if needs_grad:
+        if _bn_train is not None:
+            # training: batch-statistics BatchNorm + ReLU ride in this conv's gather prologue (forward and wgrad), the
+            # backward is dgrad + one reduction + one elementwise pass (wsis_b200/train.py)
+            from wsis_b200 import train as T
+            n_feat = features.shape[0]
+            if self.inverse:
+                rb = ops._rulebook_of(indice_pairs, indice_pair_num, outids.shape[0], n_feat, False)
+            else:
+                rb = ops._rulebook_of(indice_pairs, indice_pair_num, n_feat, outids.shape[0], self.subm)
+            out_features = T.bn_relu_conv(features, _bn_train, self.weight, rb, "inv" if self.inverse else "fwd",
+                                          residual=_residual, packed=self._packed)
+        elif needs_grad:
             assert _prologue is None and _residual is None, "fusion hooks are inference-only"
             fn = Fsp.indice_subm_conv if self.subm else (Fsp.indice_inverse_conv if self.inverse else Fsp.indice_conv)
             out_features = fn(features, self.weight, indice_pairs.to(device), indice_pair_num, outids.shape[0])

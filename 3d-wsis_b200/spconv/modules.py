@@ -112,12 +112,41 @@ class SparseSequential(SparseModule):
                 and type(act) is nn.ReLU and isinstance(input, spconv.SparseConvTensor) and input.features.is_cuda
                 and input.features.dtype == torch.float32 and input.indices.shape[0] != 0)
 
+    def _trainable(self, mods, i, input):
+        """BatchNorm1d(training) -> ReLU [-> sparse conv (not 1x1)] under autograd on CUDA fp32 features: 2 = with
+        the conv behind it, 1 = BatchNorm + ReLU only, 0 = no."""
+        if i + 1 >= len(mods) or not torch.is_grad_enabled():
+            return 0
+        from wsis_b200 import train as T
+        if not T.FUSED:
+            return 0
+        bn, act = mods[i], mods[i + 1]
+        if not (isinstance(bn, nn.BatchNorm1d) and bn.training and type(act) is nn.ReLU
+                and isinstance(input, spconv.SparseConvTensor) and input.features.is_cuda
+                and input.features.dtype == torch.float32 and input.indices.shape[0] > 1):
+            return 0
+        if i + 2 < len(mods) and isinstance(mods[i + 2], spconv.conv.SparseConvolution) and not mods[i + 2].conv1x1 \
+                and mods[i + 2].bias is None:
+            return 2
+        return 1
+
     def forward(self, input):
         mods = list(self._modules.items())
         vals = [m for _, m in mods]
         i = 0
         while i < len(mods):
             k, module = mods[i]
+            tr = self._trainable(vals, i, input)
+            if tr == 2:
+                self._sparity_dict[mods[i + 2][0]] = input.sparity
+                input = vals[i + 2](input, _bn_train=module)
+                i += 3
+                continue
+            if tr == 1:
+                from wsis_b200 import train as T
+                input.features = T.batch_norm_train(input.features, module, True)
+                i += 2
+                continue
             if self._fusable(vals, i, input):
                 scale, shift = _fold_bn(module)
                 self._sparity_dict[mods[i + 2][0]] = input.sparity

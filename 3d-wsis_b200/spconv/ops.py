@@ -137,10 +137,10 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     if inverse:
         rb = _rulebook_of(indice_pairs, indice_pair_num, n_out, n_feat, False)
         din = W.sparse_conv(out_bp, w3, rb.nbr_out, n_feat, 0, True, tiles=rb.tiles_out() if use_tiles else None)
-        dw = W.sparse_conv_wgrad(features, rb.nbr_in, n_out, 0, out_bp, K, Cin, Cout)
+        dw = W.sparse_conv_wgrad(features, rb.nbr_in, n_out, 0, out_bp, K, Cin, Cout, order=rb.order_hint("in"))
     else:
         rb = _rulebook_of(indice_pairs, indice_pair_num, n_feat, n_out, subm)
         fmap, fflip = rb.fwd_map()
         din = W.sparse_conv(out_bp, w3, rb.nbr_in, n_feat, 0, True, tiles=rb.tiles_in() if use_tiles else None)
-        dw = W.sparse_conv_wgrad(features, fmap, n_out, fflip, out_bp, K, Cin, Cout)
+        dw = W.sparse_conv_wgrad(features, fmap, n_out, fflip, out_bp, K, Cin, Cout, order=rb.order_hint("out"))
     return din, dw.view(filters.shape)

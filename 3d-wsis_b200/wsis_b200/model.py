@@ -66,6 +66,15 @@ class ResidualBlock(SparseModule):
             res = self.i_branch(identity).features
             mid = conv1(input, _prologue=_fold_bn(bn1) + (1,))
             return conv2(mid, _prologue=_fold_bn(bn2) + (1,), _residual=res)
+        if (self.normalize_before and self.training and torch.is_grad_enabled() and input.features.is_cuda
+                and input.features.dtype == torch.float32 and input.indices.shape[0] > 1):
+            # training: batch-statistics BN+ReLU in each conv's prologue, the identity add in the second conv's epilogue
+            from . import train as T
+            bn1, _, conv1, bn2, _, conv2 = list(self.conv_branch._modules.values())
+            if T.FUSED and bn1.training and bn2.training:
+                res = self.i_branch(identity).features
+                mid = conv1(input, _bn_train=bn1)
+                return conv2(mid, _bn_train=bn2, _residual=res)
         output = self.conv_branch(input)
         output.features += self.i_branch(identity).features
         return output
@@ -229,7 +238,7 @@ class RNNGraphConvModule(nn.Module):
     def forward(self, hx):
         edgefeats = self._gci.get_buffers()[4]
         edge_index = self._gci.get_pyg_buffers()
-        weights = self._fnet(edgefeats)
+        weights = _seq(self._fnet, edgefeats)
         nc = hx.size(1)
         assert hx.dim() == 2 and weights.dim() == 2 and weights.size(1) == nc * nc
         cell = self._cell
@@ -295,14 +304,23 @@ class GraphNetwork(nn.Module):
             gc.set_info(gc_infos[i])
 
     def forward(self, input):
-        for module in self._modules.values():
-            input = module(input)
-        return input
+        return _seq(self, input)
 
 
 # ---------------------------------------------------------------------------------------------------------
 # Network (backbone_3D_WSIS.py)
 # ---------------------------------------------------------------------------------------------------------
+def _seq(seq, x):
+    """nn.Sequential forward; under autograd on CUDA, training-mode BatchNorm1d (+ReLU) runs on the batch-statistics
+    kernels of wsis_b200.train (synchronised across ranks like SyncBatchNorm)."""
+    if torch.is_grad_enabled() and x.is_cuda:
+        from . import train as T
+        return T.run_sequential(seq, x)
+    for module in seq._modules.values():
+        x = module(x)
+    return x
+
+
 def _head(norm_fn, width, out):
     return nn.Sequential(nn.Linear(width, width, bias=True), norm_fn(width), nn.ReLU(inplace=True),
                          nn.Linear(width, out))
@@ -372,7 +390,7 @@ class Network(nn.Module):
             output_feats = W.gather_rows(output.features, p2v)                        # :179 voxel -> point
         else:
             output_feats = output.features[input_map.long()]
-        ret["semantic_scores"] = self.linear(output_feats)                            # :182
+        ret["semantic_scores"] = _seq(self.linear, output_feats)                            # :182
 
         if fused:
             seg = extra_data.get("sp_index")
@@ -387,10 +405,10 @@ class Network(nn.Module):
         self.ecc.set_info(extra_data['GIs'], cuda=output_feats.is_cuda)
         ecc_outputs = self.ecc(embeddings)                                            # :191-193
 
-        ret['sp_semantic_scores'] = self.sp_sem_seg(ecc_outputs)
-        ret['pred_sp_offset_vectors'] = self.sp_offset_vector_head(ecc_outputs)
-        ret['pred_sp_occupancy'] = self.sp_occupancy_head(ecc_outputs).squeeze(-1)
-        ret['pred_sp_ins_size'] = self.sp_ins_size_head(ecc_outputs).squeeze(-1)
+        ret['sp_semantic_scores'] = _seq(self.sp_sem_seg, ecc_outputs)
+        ret['pred_sp_offset_vectors'] = _seq(self.sp_offset_vector_head, ecc_outputs)
+        ret['pred_sp_occupancy'] = _seq(self.sp_occupancy_head, ecc_outputs).squeeze(-1)
+        ret['pred_sp_ins_size'] = _seq(self.sp_ins_size_head, ecc_outputs).squeeze(-1)
 
         centers = extra_data['superpoint_cenetr_xyz']
         q, k, v = self.w_qs(ecc_outputs), self.w_ks(ecc_outputs), self.w_vs(ecc_outputs)
@@ -402,7 +420,7 @@ class Network(nn.Module):
         else:
             affinity, sp_feat = _edge_attention_torch(q, k, v, ecc_outputs, centers, edge_u, edge_v, self.fc_position)
         ret['edge_affinity'] = affinity
-        ret['sp_discriminative_feats'] = self.feature_term(sp_feat)
+        ret['sp_discriminative_feats'] = _seq(self.feature_term, sp_feat)
         return ret
 
 

@@ -194,6 +194,11 @@ class Rulebook:
             return identity_order(n, self.nbr_in.device)
         return spatial_order(coords, shape, self.batch_size)
 
+    def order_hint(self, side):
+        """Morton order of one side's rows when the coordinates are known, else None (= natural order)."""
+        coords, shape = (self.out_coords, self.out_shape) if side == "out" else (self.in_coords, self.in_shape)
+        return None if coords is None or shape is None else spatial_order(coords, shape, self.batch_size)
+
     def tiles_out(self):
         """Destination = the conv's output rows (forward of subm / strided conv, dgrad of the inverse conv)."""
         if "out" not in self._tiles:
@@ -380,8 +385,10 @@ def sparse_conv(src, weight3, map_, n_dst, flip, transpose_w=False, prologue=Non
     return dst
 
 
-def sparse_conv_wgrad(src, map_, n_dst, flip, grad_out, K, Cin, Cout, prologue=None):
-    """dW[k] = sum_r prologue(src[map[r,k']])^T grad_out[r]   -> f32[K, Cin, Cout]."""
+def sparse_conv_wgrad(src, map_, n_dst, flip, grad_out, K, Cin, Cout, prologue=None, order=None, precision=None):
+    """dW[k] = sum_r prologue(src[map[r,k']])^T grad_out[r]   -> f32[K, Cin, Cout].
+    Tensor-core kernel (csrc/wgrad_umma.cu) when the shape allows it and the precision is not "simt"; `order` = the
+    Morton order of the destination rows (TileMap.order) when the caller has one."""
     src = _cuda(src, "features").contiguous()
     grad_out = grad_out.contiguous()
     dW = torch.empty((K, Cin, Cout), dtype=torch.float32, device=src.device)
@@ -389,6 +396,12 @@ def sparse_conv_wgrad(src, map_, n_dst, flip, grad_out, K, Cin, Cout, prologue=N
     relu = 0
     if prologue is not None:
         scale, shift, relu = prologue
+        scale, shift = scale.contiguous(), shift.contiguous()
+    precision = precision or _PRECISION
+    if precision != "simt" and lib().value("wsis_conv_wgrad_umma_supported", K, Cin, Cout):
+        lib().call("wsis_conv_wgrad_umma", _ptr(src), _ptr(map_), _ptr(order), n_dst, K, int(flip), _ptr(grad_out), Cin,
+                   Cout, _ptr(scale), _ptr(shift), int(relu), 3 if precision == "fp32" else 1, _ptr(dW), _stream())
+        return dW
     lib().call("wsis_conv_wgrad", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(grad_out), Cin, Cout, _ptr(scale),
                _ptr(shift), int(relu), _ptr(dW), _stream())
     return dW

@@ -20,7 +20,10 @@ DEFAULT_MODEL_CFG = dict(input_channel=3, use_coords=True, blocks=5, block_reps=
 
 # tensors the forward needs on the device (what train_scannetv2.py:149-172 moves with .cuda())
 _DEVICE_KEYS = ("locs", "locs_float", "feats", "superpoint", "edge_u_list", "edge_v_list", "ecc_edge_index",
-                "ecc_edgefeats", "seed_label")
+                "ecc_edgefeats", "seed_label",
+                # training labels (train_scannetv2.py:155-167)
+                "semantic_labels", "instance_labels", "superpoint_semantic_labels", "superpoint_instance_labels",
+                "superpoint_offset_vector", "superpoint_instance_voxel_num", "superpoint_instance_size")
 
 
 def build_network(cfg=None, seed=123, device="cuda"):

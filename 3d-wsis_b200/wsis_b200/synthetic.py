@@ -126,7 +126,38 @@ def make_shell(n_floor=(400, 300), wall=(400, 75)):
     return np.concatenate([np.zeros((c.shape[0], 1), np.int64), c], 1), [n_floor[0], n_floor[1], 128]
 
 
-def collate(scenes, full_scale=128):
+def training_labels(scene, labelled_fraction=0.3, ignore=-100):
+    """Weak labels of one scene in the form the reference's collate_fn hands to the loss (scannetv2_dataset.py:
+    362-440): per-superpoint semantic / instance label (-100 = unlabelled; the seed superpoints plus a
+    `labelled_fraction` of pseudo-labelled ones, as in the middle of training), the offset from the superpoint centre
+    to its instance centre, log(#voxels of the instance) and the instance's size; point labels = the label of the
+    point's superpoint."""
+    rng = np.random.default_rng(int(scene["num_superpoints"]) * 7919 + 17)
+    S = scene["num_superpoints"]
+    sp, xyz = scene["superpoint"], scene["xyz"].astype(np.float64)
+    cnt = np.maximum(np.bincount(sp, minlength=S), 1)
+    centers = np.stack([np.bincount(sp, weights=xyz[:, d], minlength=S) for d in range(3)], 1) / cnt[:, None]
+    inst = scene["sp_instance"]
+    n_inst = int(inst.max()) + 1
+    pinst = inst[sp]
+    icnt = np.maximum(np.bincount(pinst, minlength=n_inst), 1)
+    icenter = np.stack([np.bincount(pinst, weights=xyz[:, d], minlength=n_inst) for d in range(3)], 1) / icnt[:, None]
+    vox = np.unique(np.concatenate([pinst[:, None], scene["locs"]], 1), axis=0)
+    ivox = np.maximum(np.bincount(vox[:, 0], minlength=n_inst), 1)
+    lo = np.full((n_inst, 3), np.inf)
+    hi = np.full((n_inst, 3), -np.inf)
+    np.minimum.at(lo, pinst, xyz)
+    np.maximum.at(hi, pinst, xyz)
+    isize = np.linalg.norm(np.where(np.isfinite(hi - lo), hi - lo, 0.0), axis=1)
+    labelled = (scene["seed_label"] != ignore) | (rng.random(S) < labelled_fraction)
+    sp_sem = np.where(labelled, scene["sp_class"], ignore).astype(np.int64)
+    sp_ins = np.where(labelled, inst, ignore).astype(np.int64)
+    return dict(sp_sem=sp_sem, sp_ins=sp_ins, sp_offset=(icenter[inst] - centers).astype(np.float32),
+                sp_voxnum=np.log(ivox[inst].astype(np.float32)), sp_size=isize[inst].astype(np.float32),
+                pt_sem=sp_sem[sp], pt_ins=sp_ins[sp])
+
+
+def collate(scenes, full_scale=128, with_labels=False):
     """Batch scenes the way collate_fn does (scannetv2_dataset.py:343-474): batch index in locs[:,0], superpoint
     and edge ids offset per scene, spatial_shape = clip(max+1, full_scale[0], None) (:445), edges for the ECC
     network sorted by target (ecc/GraphConvInfo.py:50-76).  CPU tensors, ready for pin_memory()."""
@@ -148,7 +179,19 @@ def collate(scenes, full_scale=128):
     eu, ev, ef = np.concatenate(eu), np.concatenate(ev), np.concatenate(ef)
     order = np.argsort(ev, kind="stable")
     spatial_shape = np.clip(locs.max(0)[1:] + 1, full_scale, None)
-    return dict(
+    extra = {}
+    if with_labels:
+        labs, ibase = [training_labels(s) for s in scenes], 0
+        for s, lab in zip(scenes, labs):                      # instance ids are unique across the batch (:386-389)
+            for k in ("sp_ins", "pt_ins"):
+                lab[k] = np.where(lab[k] >= 0, lab[k] + ibase, lab[k])
+            ibase += int(s["sp_instance"].max()) + 1
+        cat = lambda k: torch.from_numpy(np.concatenate([lab[k] for lab in labs]))  # noqa: E731
+        extra = dict(semantic_labels=cat("pt_sem"), instance_labels=cat("pt_ins"),
+                     superpoint_semantic_labels=cat("sp_sem"), superpoint_instance_labels=cat("sp_ins"),
+                     superpoint_offset_vector=cat("sp_offset"), superpoint_instance_voxel_num=cat("sp_voxnum"),
+                     superpoint_instance_size=cat("sp_size"))
+    return dict(extra, 
         locs=torch.from_numpy(locs), locs_float=torch.from_numpy(np.concatenate(xyz)),
         feats=torch.from_numpy(np.concatenate(feats_rgb)), superpoint=torch.from_numpy(np.concatenate(sp)),
         edge_u_list=torch.from_numpy(eu), edge_v_list=torch.from_numpy(ev),

@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE.json configs[1] (the headline metric); train: configs[2], one data-parallel "
+                         "training step (forward + MultiTaskLoss + backward + NCCL gradient all-reduce + AdamW) per batch")
     ap.add_argument("--scenes", type=int, default=4, help="scenes per batch (configs[1]: 4)")
     ap.add_argument("--points", type=int, default=150000, help="points per scene")
     ap.add_argument("--shape", default="scannet", choices=["scannet", "s3dis"],
@@ -75,13 +78,13 @@ def workload_config(args, extra=None):
     return cfg
 
 
-def make_batches(args, rank, n_batches):
+def make_batches(args, rank, n_batches, with_labels=False):
     from wsis_b200 import synthetic
     out = []
     for b in range(n_batches):
         mk = synthetic.make_room_s3dis if args.shape == "s3dis" else synthetic.make_scene
         scenes = [mk(2000 + 100 * rank + 10 * b + i, n_points=args.points) for i in range(args.scenes)]
-        out.append(synthetic.collate(scenes))
+        out.append(synthetic.collate(scenes, with_labels=with_labels))
     return out
 
 
@@ -432,13 +435,203 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# training step (BASELINE.json configs[2])
+# ---------------------------------------------------------------------------------------------------------
+TRAIN_METRIC = "scenes/sec training step (ScanNet-shape, fwd+loss+bwd+gradient all-reduce+AdamW)"
+
+
+def cpu_train_pass(args, n_steps, warmup, want=None):
+    """The reference's CPU kernels under autograd (indiceConv + indiceConvBackward, torch BatchNorm in training mode,
+    the MultiTaskLoss) on ONE scene of the batch per step."""
+    from oracle import cpu_pipeline
+    from wsis_b200 import pipeline, synthetic, train as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net = pipeline.build_network(seed=123, device="cpu").train()
+    batch = synthetic.collate([synthetic.make_scene(2000, n_points=args.points)], with_labels=True)
+    crit = T.MultiTaskLoss()
+    times, stages, loss = [], None, None
+    for it in range(warmup + n_steps):
+        net.zero_grad(set_to_none=True)
+        if it == 0 and want is not None:                # parity sample: the very first step from the seed-123 weights
+            t0 = time.perf_counter()
+            loss, parts, _, stages = cpu_pipeline.train_step(net, batch, crit)
+            want.update(loss=float(loss), grads={n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None},
+                        batch=batch)
+        else:
+            t0 = time.perf_counter()
+            loss, parts, _, stages = cpu_pipeline.train_step(net, batch, crit)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": n_steps / total, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "1 scene of %d pts per step (of the %d-scene batch): forward + MultiTaskLoss + backward on the "
+                      "reference's CPU kernels (oracle/_ref indiceConv/indiceConvBackward, torch BatchNorm), no optimizer; "
+                      "%d timed steps after %d warm-up; threads=%d; stages(s)=%s"
+                      % (args.points, args.scenes, n_steps, warmup, cores, {k: round(v, 3) for k, v in stages.items()}),
+            "ms_per_step": 1e3 * total / n_steps, "steps": n_steps, "warmup": warmup}
+
+
+def run_train_reference(args, rank):
+    if rank != 0:
+        return
+    n = max(1, min(args.steps, 6))
+    cb = cpu_train_pass(args, n, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": TRAIN_METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": cb["steps"], "warmup": cb["warmup"], "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, {"mode": "train", "scenes_per_step": 1, "l2": "n/a (host)"}),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_train(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from wsis_b200 import ops as W
+    from wsis_b200 import pipeline
+    from wsis_b200 import train as T
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    W.set_precision(args.precision)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    net = pipeline.build_network(seed=123, device="cuda").train()
+    step = T.TrainStep(net)
+    n_batches = 2
+    host = [pipeline.pin_batch(b) for b in make_batches(args, rank, n_batches, with_labels=True)]
+    dev = [pipeline.to_device(b)[0] for b in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    pool = torch.empty(16 << 30, dtype=torch.uint8, device="cuda")
+    del pool
+    for b in range(n_batches):
+        step(dev[b])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        step(dev[i % n_batches])
+        return None
+
+    def step_e2e(i):
+        db, nb = pipeline.to_device(host[i % n_batches])
+        loss, _ = step(db)
+        out = loss.to("cpu")
+        return nb, out.numel() * out.element_size()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = W.launch_count()
+        evs, extra = [], None
+        for i in range(steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            extra = fn(warmup + i)
+            e.record()
+            evs.append((s, e))
+        barrier()
+        per_step = [s.elapsed_time(e) for s, e in evs]
+        total = sum(per_step) * 1e-3
+        if world > 1:
+            t = torch.tensor([total], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total, W.launch_count() - l0, extra, per_step
+
+    clocks.wait_ready()
+    t_begin = time.time()
+    t_res, launches, _, ms_res = timed(step_resident, args.steps, args.warmup)
+    t_end = time.time()
+    t_e2e, _, io, ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    # stage split of one step (CUDA events on the launching stream; outside the timed regions)
+    stages = None
+    if rank == 0:
+        from wsis_b200.train import loss_inputs
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        flush.zero_()
+        step.opt.zero_grad()
+        evs[0].record()
+        with torch.enable_grad():
+            ret, _ = pipeline.forward_batch(net, dev[0])
+            evs[1].record()
+            loss, _ = step.loss(loss_inputs(ret, dev[0]), step.epoch)
+            evs[2].record()
+            loss.backward()
+        evs[3].record()
+    if world > 1:
+        dist.all_reduce(step.opt.bucket.flat)
+    if rank == 0:
+        evs[4].record()
+        step.opt.step(grad_scale=1.0 / world)
+        evs[5].record()
+        torch.cuda.synchronize()
+        names = ["forward", "loss", "backward", "grad_allreduce", "adamw"]
+        stages = {n: round(evs[i].elapsed_time(evs[i + 1]), 3) for i, n in enumerate(names)}
+    launches_total = count_all_launches(lambda: step_resident(0)) if rank == 0 else None
+    cpu = parity_obj = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        want = {}
+        cb = cpu_train_pass(args, 2, 1, want=want)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        net2 = pipeline.build_network(seed=123, device="cuda").train()
+        chk = T.TrainStep(net2)
+        loss_d, _ = chk(pipeline.to_device(want["batch"])[0], optimize=False)
+        worst, wname = 0.0, None
+        gmax = max(float(r.abs().max()) for r in want["grads"].values())
+        for name, p in net2.named_parameters():
+            if name in want["grads"]:
+                r = want["grads"][name]     # relative to max(own largest gradient, 1e-4 of the network's largest)
+                d = float((p.grad.cpu() - r).abs().max()) / max(float(r.abs().max()), 1e-4 * gmax)
+                if d > worst:
+                    worst, wname = d, name
+        parity_obj = {"loss_device": float(loss_d), "loss_reference_cpu": want["loss"],
+                      "loss_rel": abs(float(loss_d) - want["loss"]) / abs(want["loss"]),
+                      "max_param_grad_rel": float("%.3g" % worst), "worst_param": wname,
+                      "against": "the reference's CPU kernels under autograd on 1 scene of %d pts, same weights" % args.points}
+    clocks.terminate()
+    clk = clocks.summary(t_begin, t_end)
+    if rank == 0:
+        scenes = args.scenes * args.steps * world
+        line = {"metric": TRAIN_METRIC, "value": scenes / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
+                "ms_per_step_min_median_max": [round(min(ms_res), 3), round(statistics.median(ms_res), 3), round(max(ms_res), 3)],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate)",
+                          "bf16": "bf16 operands on tcgen05, fp32 accumulate", "simt": "f32"}[args.precision],
+                "data": "synthetic",
+                "config": workload_config(args, {"mode": "train", "parallelism": "data parallel x%d: synchronised BatchNorm "
+                                                 "statistics + ONE NCCL all-reduce of the flat gradient bucket (%d floats) per step"
+                                                 % (world, step.opt.flat_p.numel()), "precision": args.precision,
+                                                 "optimizer": "AdamW lr 1e-3 wd 1e-4, ECC gradient clamp"}),
+                "clocks": clk,
+                "e2e": {"value": scenes / t_e2e, "unit": UNIT, "h2d_bytes_per_step": io[0], "d2h_bytes_per_step": io[1],
+                        "ms_per_step": 1e3 * t_e2e / args.steps,
+                        "ms_per_step_min_median_max": [round(min(ms_e2e), 3), round(statistics.median(ms_e2e), 3), round(max(ms_e2e), 3)]},
+                "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+                "launches_total_per_step": launches_total, "stages_ms": stages, "roofline": None,
+                "cpu_baseline": cpu, "parity": parity_obj}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.mode == "train":
+            run_train_reference(args, rank)
+        else:
+            run_reference(args, rank, world)
         return
     if world > 1:
         import torch.distributed as dist
@@ -446,7 +639,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        (run_train if args.mode == "train" else run_ours)(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -269,6 +269,49 @@ int wsis_random_walk(const int64_t *edge_u, const int64_t *edge_v, const float *
                      const int32_t *seed_label, const int32_t *pred, const float *conf, int class_num, int iterations,
                      int32_t *pseudo, double *score, void *ws, wsis_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------- */
+/* training step (train_scannetv2.py:200-252): batch-statistics BatchNorm around the sparse convs,  */
+/* fused AdamW                                                                                     */
+/* ---------------------------------------------------------------------------------------------- */
+/* Weight gradient on the tensor cores (tcgen05, both operands MN-major): the contraction over the rows of
+ * indiceConvBackward's mm(in^T, dout) (spconv_ops.h:395-415), output-stationary like wsis_conv_umma:
+ *   dW[k][ci][co] = sum_r prologue(src[map[r, flip ? K-1-k : k], ci]) * g[r, co]
+ * `order` (int32[tile_pad(n_dst)] from wsis_spatial_order, or NULL) only changes the order in which destination
+ * rows are visited (locality); precision 3 = bf16x3 split operands (fp32 contract), 1 = bf16 operands.
+ * Needs 5 <= K <= 32, Cin % 32 == 0, Cout % 32 == 0 (wsis_conv_wgrad_umma_supported); otherwise use wsis_conv_wgrad. */
+int wsis_conv_wgrad_umma_supported(int K, int Cin, int Cout);
+int wsis_conv_wgrad_umma(const float *src, const int32_t *map, const int32_t *order, int64_t n_dst, int K, int flip,
+                         const float *g, int Cin, int Cout, const float *in_scale, const float *in_shift, int in_relu,
+                         int precision, float *dW, wsis_stream_t stream);
+
+/* BatchNorm1d in training mode over x float[N,C] (torch.nn.BatchNorm1d / SyncBatchNorm of
+ * sparse_unet3d.py:135-171, train_scannetv2.py:736).  The normalisation itself is applied by the consumer
+ * (wsis_conv_umma's in_scale/in_shift/in_relu prologue, or wsis_affine_relu); these calls are the reductions.
+ *   wsis_bn_stats:      sums double[2C+1] = (sum x | sum x^2 | N).  With synchronised statistics the caller
+ *                       all-reduces `sums` across ranks before wsis_bn_finalize.
+ *   wsis_bn_finalize:   stat float[4,C] = mean | invstd | scale = gamma*invstd | shift = beta - mean*scale;
+ *                       running_mean/var (NULL = skip) updated with `momentum` (unbiased variance).
+ *   wsis_bn_bwd_reduce: da = gradient w.r.t. y = relu?(x*scale+shift); dy = da*[y > 0] when relu;
+ *                       sums double[2C] = (sum dy | sum dy*xhat); dgamma/dbeta float[C] = the LOCAL sums
+ *                       (NULL = skip).  All-reduce `sums` for synchronised statistics.
+ *   wsis_bn_bwd_apply:  dx = scale*(dy - sums[c]/count - xhat*sums[C+c]/count) (+ extra[i] when extra != NULL);
+ *                       `count` points at the (global) row count, i.e. element 2C of the forward sums.
+ * ws: wsis_bn_ws_bytes(N, C).  Reductions are two-stage in a fixed order (deterministic). */
+int64_t wsis_bn_ws_bytes(int64_t N, int C);
+int wsis_bn_stats(const float *x, int64_t N, int C, void *ws, double *sums, wsis_stream_t stream);
+int wsis_bn_finalize(const double *sums, int C, const float *gamma, const float *beta, float eps, float momentum,
+                     float *running_mean, float *running_var, float *stat, wsis_stream_t stream);
+int wsis_bn_bwd_reduce(const float *x, const float *da, int64_t N, int C, const float *stat, int relu, void *ws,
+                       double *sums, float *dgamma, float *dbeta, wsis_stream_t stream);
+int wsis_bn_bwd_apply(const float *x, const float *da, int64_t N, int C, const float *stat, int relu,
+                      const double *sums, const double *count, const float *extra, float *dx, wsis_stream_t stream);
+/* torch.optim.AdamW (train_scannetv2.py:93-94) over flat buffers, `step` counts from 1.  The gradient is first
+ * multiplied by grad_scale (1/world for a sum-all-reduced bucket) and elements [clamp_begin, clamp_end) are
+ * clamped to [-1, 1] (the ECC gradient clamp, train_scannetv2.py:246-249). */
+int wsis_adamw_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int64_t step, float grad_scale, int64_t clamp_begin,
+                    int64_t clamp_end, wsis_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

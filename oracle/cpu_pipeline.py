@@ -20,10 +20,28 @@ from . import oracle as orc
 from . import ref_spconv
 
 
+class _RefConvFn(torch.autograd.Function):
+    """Autograd over the reference's CPU kernels: forward = indiceConv, backward = indiceConvBackward
+    (spconv_ops.h:253-433), exactly the pairing of modules/lib/spconv/spconv/functional.py:21-117."""
+
+    @staticmethod
+    def forward(ctx, feats, weight, pairs, num, n_out, inverse, subm):
+        ctx.save_for_backward(feats, weight, pairs, num)
+        ctx.inverse, ctx.subm = inverse, subm
+        return ref_spconv.indice_conv(feats, weight, pairs, num, n_out, inverse, subm)
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, weight, pairs, num = ctx.saved_tensors
+        din, dw = ref_spconv.indice_conv_backward(feats, weight, g.contiguous(), pairs, num, ctx.inverse, ctx.subm)
+        return din, dw, None, None, None, None, None
+
+
 class CpuSpconv:
     """get_indice_pairs + indice_conv on the CPU with a per-key rulebook cache (conv.py:140-152)."""
 
-    def __init__(self, prefer_reference=True):
+    def __init__(self, prefer_reference=True, train=False):
+        self.train = train
         self.use_ref = prefer_reference and ref_spconv.available()
         self.kind = "reference" if self.use_ref else "port"
         self.rulebooks = {}
@@ -51,7 +69,10 @@ class CpuSpconv:
 
     def conv(self, feats, weight, pairs, num, n_out, inverse=False, subm=False):
         t0 = time.perf_counter()
-        if self.use_ref:
+        if self.train:
+            assert self.use_ref, "the CPU training step needs oracle/_ref (the reference's backward kernels)"
+            out = _RefConvFn.apply(feats, weight, pairs, num, n_out, inverse, subm)
+        elif self.use_ref:
             out = ref_spconv.indice_conv(feats, weight, pairs, num, n_out, inverse, subm)
         else:
             out = torch.from_numpy(orc.indice_conv(feats.numpy(), weight.numpy(), pairs.numpy(), num.numpy(), n_out, inverse))
@@ -60,6 +81,8 @@ class CpuSpconv:
 
 
 def _bn_relu(bn, x):
+    if bn.training:      # training step: the module itself (batch statistics, running-stat update), as the reference does
+        return F.relu(bn(x))
     return F.relu(F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps))
 
 
@@ -102,13 +125,34 @@ def _scatter(src, index, reduce, S):
     return out
 
 
-@torch.no_grad()
 def forward(net, batch, prefer_reference=True, keep=None):
+    with torch.no_grad():
+        return _forward(net, batch, prefer_reference, keep, False)
+
+
+def train_step(net, batch, criterion, epoch=121):
+    """One CPU training step body (train_scannetv2.py:149-244: forward, MultiTaskLoss, backward) on the reference's
+    CPU kernels with torch BatchNorm in training mode.  `net` = a CPU, train-mode network; `criterion` = a
+    MultiTaskLoss.  Returns (loss, loss parts, ret, stage timings).  Gradients are left in the parameters' .grad."""
+    T0 = time.perf_counter()
+    ret, T, kind = _forward(net, batch, True, None, True)
+    t0 = time.perf_counter()
+    from wsis_b200.train import loss_inputs           # pure dict plumbing (train_scannetv2.py:211-231)
+    loss, parts = criterion(loss_inputs(ret, batch), epoch)
+    T["loss"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    loss.backward()
+    T["backward"] = time.perf_counter() - t0
+    T["total"] = time.perf_counter() - T0
+    return loss.detach(), parts, ret, T
+
+
+def _forward(net, batch, prefer_reference, keep, train):
     """CPU forward of one collated batch with `net` (a CPU, eval-mode wsis_b200.model.Network).
     Returns (ret dict of torch CPU tensors, stage timings dict, kind).  When `keep` is a dict it receives what the
     parity checks compare besides the outputs: the nine rulebooks (key -> (in coords, out coords, pairs, num)), the
     voxelization maps and the U-Net output features."""
-    sp = CpuSpconv(prefer_reference)
+    sp = CpuSpconv(prefer_reference, train)
     T = {}
     t0 = time.perf_counter()
     voxel_locs, p2v, v2p = (torch.from_numpy(a) for a in orc.voxelization_idx(batch["locs"].numpy(), batch["batch_size"], 4))

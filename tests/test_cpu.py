@@ -703,3 +703,37 @@ def test_bench_clock_sampler_summary_window_and_reasons():
     assert cs.summary(100.0, 101.0)["samples"] == 3               # nothing inside: falls back to the last samples
     cs.proc = None
     assert cs.summary(0, 1)["reasons"] == ["nvidia-smi unavailable"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training step: loss against the reference's own MultiTaskLoss, optimizer and data-parallel plumbing
+# ---------------------------------------------------------------------------------------------------------
+def _loss_case(golden_dir, device="cpu"):
+    g = np.load(os.path.join(golden_dir, "loss_batch2.npz"))
+    pred = ("semantic_scores", "sp_semantic_scores", "pred_sp_offset_vectors", "pred_sp_occupancy", "pred_sp_ins_size",
+            "sp_discriminative_feats")
+    t = {k: torch.from_numpy(g[k]).to(device) for k in g.files if g[k].ndim > 0 and not k.startswith("grad_")}
+    for k in pred:
+        t[k].requires_grad_(True)
+    return g, t, pred
+
+
+@pytest.mark.parametrize("tag,epoch", [("early", 1), ("joint", 121)])
+def test_vectorised_loss_matches_reference_golden(golden_dir, tag, epoch):
+    """wsis_b200.train.MultiTaskLoss (one vectorised formulation for the batch) against the reference's own
+    MultiTaskLoss executed by tests/golden/make_golden_loss.py (losses_3D_WSIS.py:43-230, per-scene Python loop):
+    every term, the total and the gradient w.r.t. every network output."""
+    from wsis_b200 import train as T
+    g, t, pred = _loss_case(golden_dir)
+    ret = {k: t[k] for k in pred}
+    loss, parts = T.MultiTaskLoss()(T.loss_inputs(ret, t), epoch)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_" + tag])) < 1e-5 * abs(float(g["loss_" + tag]))
+    for k, v in parts.items():
+        assert abs(v.item() - float(g["%s_%s" % (k, tag)])) < 2e-5 * max(1.0, abs(float(g["%s_%s" % (k, tag)]))), k
+    for k in pred:
+        ref = g["grad_%s_%s" % (k, tag)] if ("grad_%s_%s" % (k, tag)) in g.files else None
+        if ref is None:
+            assert t[k].grad is None or float(t[k].grad.abs().max()) == 0.0
+        else:
+            assert np.abs(t[k].grad.numpy() - ref).max() < 1e-5 * max(np.abs(ref).max(), 1e-12), k
