@@ -24,7 +24,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kBnThreads)
 bn_colsum_kernel(const float *__restrict__ x, const float *__restrict__ da, int64_t N, int C,
                  const float *__restrict__ stat /* mean | invstd | scale | shift, [4][C] */, int relu,
-                 float *__restrict__ partial /* [gridDim.x][2][C] */) {
+                 float *__restrict__ partial /* [gridDim.x][3C + 1]: sum1[C] | sum2[C] | pivot[C] | rows */) {
   extern __shared__ float sm[];  // [rows_per_pass][2][C]
   const int tpr = (C + 3) / 4;                  // threads per row (4 channels each)
   const int rpp = kBnThreads / tpr;             // rows per pass
@@ -89,10 +89,20 @@ bn_colsum_kernel(const float *__restrict__ x, const float *__restrict__ da, int6
       }
   }
   __syncthreads();
+  float *pout = partial + (int64_t)blockIdx.x * (3 * C + 1);
   for (int i = threadIdx.x; i < 2 * C; i += kBnThreads) {
     float acc = 0.f;
     for (int r = 0; r < rpp; ++r) acc += sm[r * 2 * C + i];
-    partial[(int64_t)blockIdx.x * 2 * C + i] = acc;
+    pout[i] = acc;
+  }
+  if (MODE == 0) {
+    const int64_t r0 = (int64_t)blockIdx.x * rpp;
+    for (int c = threadIdx.x; c < C; c += kBnThreads) pout[2 * C + c] = r0 < N ? x[r0 * C + c] : 0.f;
+    if (threadIdx.x == 0) {                  // rows r0 + j + k * gridDim.x * rpp < N, j < rpp (< 2^24: exact in fp32)
+      int64_t nb = 0;
+      for (int j = 0; j < rpp && r0 + j < N; ++j) nb += (N - (r0 + j) - 1) / ((int64_t)gridDim.x * rpp) + 1;
+      pout[3 * C] = (float)nb;
+    }
   }
 }
 
@@ -111,16 +121,12 @@ bn_combine_kernel(const float *__restrict__ partial, int nblocks, int C, double 
     const int c = i < C ? i : i - C;
     double acc = 0.0;
     for (int b = lane; b < nblocks; b += 32) {
+      const float *pb = partial + (int64_t)b * (3 * C + 1);
       if (x) {
-        int64_t r0 = (int64_t)b * rpp;
-        if (r0 >= N) continue;
-        double nb = 0.0;                       // rows r0 + j + k * nblocks * rpp < N, j < rpp
-        for (int j = 0; j < rpp && r0 + j < N; ++j) nb += (double)((N - (r0 + j) - 1) / ((int64_t)nblocks * rpp) + 1);
-        double p = (double)x[r0 * C + c];
-        double s1 = (double)partial[(int64_t)b * 2 * C + c], s2 = (double)partial[(int64_t)b * 2 * C + C + c];
+        const double nb = (double)pb[3 * C], p = (double)pb[2 * C + c], s1 = (double)pb[c], s2 = (double)pb[C + c];
         acc += i < C ? s1 + nb * p : s2 + 2.0 * p * s1 + nb * p * p;
       } else {
-        acc += (double)partial[(int64_t)b * 2 * C + i];
+        acc += (double)pb[i];
       }
     }
 #pragma unroll
@@ -158,21 +164,54 @@ __global__ void bn_finalize_kernel(const double *__restrict__ sums, int C, const
   }
 }
 
-__global__ void __launch_bounds__(256)
+// thread (row slot, channel quad) like bn_colsum_kernel: the per-channel constants are computed once per thread
+__global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ da, int64_t N, int C,
                     const float *__restrict__ stat, int relu, const double *__restrict__ sums,
                     const double *__restrict__ count, const float *__restrict__ extra, float *__restrict__ dx) {
-  const int64_t total = N * C;
+  const int tpr = (C + 3) / 4, rpp = kBnThreads / tpr;
+  const int tr = threadIdx.x / tpr, c0 = (threadIdx.x % tpr) * 4;
+  if (tr >= rpp) return;
   const double n = *count;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    float xv = x[i];
-    float scale = __ldg(stat + 2 * C + c);
-    float dy = (relu && fmaf(xv, scale, __ldg(stat + 3 * C + c)) <= 0.f) ? 0.f : da[i];
-    float xhat = (xv - __ldg(stat + c)) * __ldg(stat + C + c);
-    float m1 = (float)(sums[c] / n), m2 = (float)(sums[C + c] / n);
-    float v = scale * (dy - m1 - xhat * m2);
-    dx[i] = extra ? v + extra[i] : v;
+  float mean[4], invstd[4], scale[4], shift[4], m1[4], m2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = min(c0 + j, C - 1);
+    mean[j] = stat[c], invstd[j] = stat[C + c], scale[j] = stat[2 * C + c], shift[j] = stat[3 * C + c];
+    m1[j] = (float)(sums[c] / n), m2[j] = (float)(sums[C + c] / n);
+  }
+  const bool vec = (C % 4 == 0);
+  for (int64_t r = (int64_t)blockIdx.x * rpp + tr; r < N; r += (int64_t)gridDim.x * rpp) {
+    float xv[4], gv[4], ev[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+    if (vec) {
+      const float4 t = *reinterpret_cast<const float4 *>(x + r * C + c0), g = *reinterpret_cast<const float4 *>(da + r * C + c0);
+      xv[0] = t.x, xv[1] = t.y, xv[2] = t.z, xv[3] = t.w, gv[0] = g.x, gv[1] = g.y, gv[2] = g.z, gv[3] = g.w;
+      if (extra) {
+        const float4 e = *reinterpret_cast<const float4 *>(extra + r * C + c0);
+        ev[0] = e.x, ev[1] = e.y, ev[2] = e.z, ev[3] = e.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool in = c0 + j < C;
+        xv[j] = in ? x[r * C + c0 + j] : 0.f;
+        gv[j] = in ? da[r * C + c0 + j] : 0.f;
+        if (extra && in) ev[j] = extra[r * C + c0 + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dy = (relu && fmaf(xv[j], scale[j], shift[j]) <= 0.f) ? 0.f : gv[j];
+      const float xhat = (xv[j] - mean[j]) * invstd[j];
+      o[j] = scale[j] * (dy - m1[j] - xhat * m2[j]) + ev[j];
+    }
+    if (vec) {
+      *reinterpret_cast<float4 *>(dx + r * C + c0) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + j < C) dx[r * C + c0 + j] = o[j];
+    }
   }
 }
 
@@ -210,7 +249,7 @@ extern "C" {
 
 int64_t wsis_bn_ws_bytes(int64_t N, int C) {
   int rpp;
-  return (int64_t)bn_grid(N, C, &rpp) * 2 * C * sizeof(float);
+  return (int64_t)bn_grid(N, C, &rpp) * (3 * C + 1) * sizeof(float);
 }
 
 int wsis_bn_stats(const float *x, int64_t N, int C, void *ws, double *sums, wsis_stream_t stream) {
@@ -246,9 +285,10 @@ int wsis_bn_bwd_reduce(const float *x, const float *da, int64_t N, int C, const 
 int wsis_bn_bwd_apply(const float *x, const float *da, int64_t N, int C, const float *stat, int relu,
                       const double *sums, const double *count, const float *extra, float *dx, wsis_stream_t stream) {
   if (N == 0) return 0;
-  int64_t total = N * C;
-  unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
-  bn_bwd_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, da, N, C, stat, relu, sums, count, extra, dx);
+  int rpp;
+  bn_grid(N, C, &rpp);
+  unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(N, rpp), (int64_t)sm_count() * 8));
+  bn_bwd_apply_kernel<<<blocks, kBnThreads, 0, as_stream(stream)>>>(x, da, N, C, stat, relu, sums, count, extra, dx);
   WSIS_LAUNCH_OK();
   return 0;
 }

@@ -17,7 +17,8 @@ class _ConvFunction(Function):
     def _bwd(cls, ctx, grad_output):
         indice_pairs, indice_pair_num, features, filters = ctx.saved_tensors
         input_bp, filters_bp = ops.indice_conv_backward(features, filters, grad_output.contiguous(), indice_pairs,
-                                                        indice_pair_num, cls.inverse, cls.subm)
+                                                        indice_pair_num, cls.inverse, cls.subm,
+                                                        _need_input_grad=ctx.needs_input_grad[0])
         return input_bp, filters_bp, None, None, None
 
 

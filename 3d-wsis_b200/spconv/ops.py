@@ -125,8 +125,10 @@ def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_o
                          tiles=tiles() if use_tiles else None)
 
 
-def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False, subm=False):
-    """-> (input_bp, filters_bp): indiceConvBackward<T>, spconv_ops.h:351-433."""
+def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False, subm=False,
+                         _need_input_grad=True):
+    """-> (input_bp, filters_bp): indiceConvBackward<T>, spconv_ops.h:351-433.  `_need_input_grad=False` (autograd knows
+    that the features are a leaf without grad: the network's input conv) skips the data gradient and returns None."""
     if filters.dtype != torch.float32:
         raise NotImplementedError
     w3 = _w3(filters)
@@ -136,11 +138,13 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     use_tiles = W.get_precision() != "simt" and K <= 32 and W.umma_supported(Cout, Cin)
     if inverse:
         rb = _rulebook_of(indice_pairs, indice_pair_num, n_out, n_feat, False)
-        din = W.sparse_conv(out_bp, w3, rb.nbr_out, n_feat, 0, True, tiles=rb.tiles_out() if use_tiles else None)
+        din = W.sparse_conv(out_bp, w3, rb.nbr_out, n_feat, 0, True,
+                            tiles=rb.tiles_out() if use_tiles else None) if _need_input_grad else None
         dw = W.sparse_conv_wgrad(features, rb.nbr_in, n_out, 0, out_bp, K, Cin, Cout, order=rb.order_hint("in"))
     else:
         rb = _rulebook_of(indice_pairs, indice_pair_num, n_feat, n_out, subm)
         fmap, fflip = rb.fwd_map()
-        din = W.sparse_conv(out_bp, w3, rb.nbr_in, n_feat, 0, True, tiles=rb.tiles_in() if use_tiles else None)
+        din = W.sparse_conv(out_bp, w3, rb.nbr_in, n_feat, 0, True,
+                            tiles=rb.tiles_in() if use_tiles else None) if _need_input_grad else None
         dw = W.sparse_conv_wgrad(features, fmap, n_out, fflip, out_bp, K, Cin, Cout, order=rb.order_hint("out"))
     return din, dw.view(filters.shape)

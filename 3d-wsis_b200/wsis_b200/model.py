@@ -312,7 +312,10 @@ class GraphNetwork(nn.Module):
 # ---------------------------------------------------------------------------------------------------------
 def _seq(seq, x):
     """nn.Sequential forward; under autograd on CUDA, training-mode BatchNorm1d (+ReLU) runs on the batch-statistics
-    kernels of wsis_b200.train (synchronised across ranks like SyncBatchNorm)."""
+    kernels of wsis_b200.train (synchronised across ranks like SyncBatchNorm); in inference a Linear-BN-ReLU-Linear head
+    is one kernel (csrc/heads.cu)."""
+    if not torch.is_grad_enabled() and W.mlp_head_supported(seq, x):
+        return W.mlp_head(seq, x)
     if torch.is_grad_enabled() and x.is_cuda:
         from . import train as T
         return T.run_sequential(seq, x)
@@ -385,12 +388,19 @@ class Network(nn.Module):
         fused = not torch.is_grad_enabled() and not self.training and output.features.is_cuda
 
         superpoint = extra_data["superpoint"].long()
+        output_feats = None
         if fused:
             p2v = input_map if input_map.dtype == torch.int32 else input_map.int()
-            output_feats = W.gather_rows(output.features, p2v)                        # :179 voxel -> point
         else:
-            output_feats = output.features[input_map.long()]
-        ret["semantic_scores"] = _seq(self.linear, output_feats)                            # :182
+            output_feats = output.features[input_map.long()]                          # :179 voxel -> point
+        if fused and W.mlp_head_supported(self.linear, output.features):
+            # :179 + :182 in one kernel; the [N_points, 32] gathered features are never materialised (the pooling
+            # below gathers through p2v as well)
+            ret["semantic_scores"] = W.mlp_head(self.linear, output.features, gather=p2v)
+        else:
+            if output_feats is None:
+                output_feats = W.gather_rows(output.features, p2v)
+            ret["semantic_scores"] = _seq(self.linear, output_feats)                  # :182
 
         if fused:
             seg = extra_data.get("sp_index")
@@ -398,11 +408,14 @@ class Network(nn.Module):
                 S = extra_data.get("num_superpoints")
                 S = int(superpoint.max().item()) + 1 if S is None else int(S)
                 seg = W.SegmentIndex(superpoint, S)
-            embeddings = W.segment_reduce(output_feats, seg, "mean")                  # :188 superpoint pooling
+            if output_feats is None:                                                  # :179 + :188 superpoint pooling
+                embeddings = W.segment_reduce(output.features, seg, "mean", gather=p2v)
+            else:
+                embeddings = W.segment_reduce(output_feats, seg, "mean")
         else:
             embeddings = _scatter_torch(output_feats, superpoint, "mean")
 
-        self.ecc.set_info(extra_data['GIs'], cuda=output_feats.is_cuda)
+        self.ecc.set_info(extra_data['GIs'], cuda=output.features.is_cuda)
         ecc_outputs = self.ecc(embeddings)                                            # :191-193
 
         ret['sp_semantic_scores'] = _seq(self.sp_sem_seg, ecc_outputs)

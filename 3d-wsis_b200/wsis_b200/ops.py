@@ -398,6 +398,14 @@ def sparse_conv_wgrad(src, map_, n_dst, flip, grad_out, K, Cin, Cout, prologue=N
         scale, shift, relu = prologue
         scale, shift = scale.contiguous(), shift.contiguous()
     precision = precision or _PRECISION
+    if precision != "simt" and Cin < 32 and n_dst > 0 and lib().value("wsis_conv_wgrad_umma_supported", K, 32, Cout):
+        # the network's input conv (6 -> 32): zero-pad the rows to one 32-channel block and slice the result
+        pad = torch.zeros((src.shape[0], 32), dtype=torch.float32, device=src.device)
+        pad[:, :Cin] = src
+        ps = None
+        if prologue is not None:
+            ps = (torch.nn.functional.pad(scale, (0, 32 - Cin)), torch.nn.functional.pad(shift, (0, 32 - Cin)), relu)
+        return sparse_conv_wgrad(pad, map_, n_dst, flip, grad_out, K, 32, Cout, ps, order, precision)[:, :Cin, :].contiguous()
     if precision != "simt" and lib().value("wsis_conv_wgrad_umma_supported", K, Cin, Cout):
         lib().call("wsis_conv_wgrad_umma", _ptr(src), _ptr(map_), _ptr(order), n_dst, K, int(flip), _ptr(grad_out), Cin,
                    Cout, _ptr(scale), _ptr(shift), int(relu), 3 if precision == "fp32" else 1, _ptr(dW), _stream())
@@ -542,6 +550,61 @@ def edge_attention(q, k, v, ecc, centers, edge_u, edge_v, eseg, pos_mlp):
     lib().call("wsis_edge_attention", _ptr(q), _ptr(k), _ptr(v), _ptr(ecc), _ptr(centers), _ptr(edge_u), _ptr(edge_v),
                _ptr(eseg.order), _ptr(eseg.offsets), S, E, D, _ptr(pos_mlp), _ptr(aff), _ptr(sp), _stream())
     return aff, sp
+
+
+def _head_pack(head):
+    """Sequential(Linear, BatchNorm1d, ReLU, Linear) (backbone_3D_WSIS.py:57-62) -> the folded, transposed parameter
+    images wsis_mlp_head reads; cached on the module per parameter version / cache epoch."""
+    l1, bn, _, l2 = head[0], head[1], head[2], head[3]
+    ps = [l1.weight, l1.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, l2.weight, l2.bias]
+    key = tuple((p._version, p.data_ptr()) for p in ps if p is not None) + (_CACHE_EPOCH,)
+    cache = getattr(head, "_wsis_head", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+            scale = (bn.weight.float() if bn.weight is not None else torch.ones_like(inv)) * inv
+            shift = (bn.bias.float() if bn.bias is not None else torch.zeros_like(inv)) - bn.running_mean.float() * scale
+            w1t = (l1.weight.float() * scale.unsqueeze(1)).t().contiguous()             # [Cin, H]
+            b1 = l1.bias.float() if l1.bias is not None else torch.zeros_like(scale)
+            t1 = (b1 * scale + shift).contiguous()
+            cout = l2.weight.shape[0]
+            cp = lib().value("wsis_mlp_head_coutp", cout)
+            w2t = torch.zeros((l2.weight.shape[1], cp), dtype=torch.float32, device=l2.weight.device)
+            w2t[:, :cout] = l2.weight.float().t()
+            b2 = torch.zeros((cp,), dtype=torch.float32, device=l2.weight.device)
+            if l2.bias is not None:
+                b2[:cout] = l2.bias.float()
+        cache = (key, w1t, t1, w2t, b2, cout)
+        head._wsis_head = cache
+    return cache[1:]
+
+
+def mlp_head_supported(head, x):
+    """Linear(C,C) -> BatchNorm1d(eval, running stats) -> ReLU -> Linear(C, <=32) with C in {32, 64} on CUDA fp32 rows."""
+    import torch.nn as nn
+    mods = list(head._modules.values()) if hasattr(head, "_modules") else []
+    if len(mods) != 4 or not (isinstance(mods[0], nn.Linear) and isinstance(mods[1], nn.BatchNorm1d)
+                              and type(mods[2]) is nn.ReLU and isinstance(mods[3], nn.Linear)):
+        return False
+    l1, bn, _, l2 = mods
+    C = l1.in_features
+    return (C in (32, 64) and l1.out_features == C and l2.in_features == C and l2.out_features <= 32
+            and not bn.training and bn.track_running_stats and x.is_cuda and x.dtype == torch.float32
+            and x.dim() == 2 and x.shape[1] == C)
+
+
+def mlp_head(head, x, gather=None):
+    """head(x[gather]) in one kernel (csrc/heads.cu); `gather` int32[n] or None."""
+    w1t, t1, w2t, b2, cout = _head_pack(head)
+    x = _cuda(x, "head input").contiguous()
+    n = x.shape[0] if gather is None else gather.shape[0]
+    out = torch.empty((n, cout), dtype=torch.float32, device=x.device)
+    if gather is not None:
+        assert gather.dtype == torch.int32
+        gather = gather.contiguous()
+    lib().call("wsis_mlp_head", _ptr(x), _ptr(gather), n, x.shape[1], w1t.shape[1], cout, _ptr(w1t), _ptr(t1), _ptr(w2t),
+               _ptr(b2), _ptr(out), _stream())
+    return out
 
 
 def pack_ecc_gru(cell):

@@ -224,6 +224,15 @@ int wsis_segment_reduce(const float *src, const int32_t *gather, const int32_t *
 /* dst[i,:] = src[idx[i],:]  (voxel->point gather, backbone_3D_WSIS.py:179) */
 int wsis_gather_rows(const float *src, const int32_t *idx, int64_t n, int C, float *dst, wsis_stream_t stream);
 
+/* Per-row MLP head in inference: Linear -> BatchNorm1d(eval) -> ReLU -> Linear (backbone_3D_WSIS.py:57-62 over every
+ * point, :71-104 the superpoint heads) as one kernel, optionally fused with the voxel -> point gather (:179):
+ *   out[i, 0..Cout) = W2 . relu(W1' . src[gather ? gather[i] : i, :] + t1) + b2
+ * w1t float[Cin, H] = (diag(bn_scale) W1)^T, t1 float[H] = bn_scale*b1 + bn_shift, w2t float[H, coutp] = W2^T zero-padded
+ * to coutp = wsis_mlp_head_coutp(Cout) columns, b2 float[coutp].  (Cin, H) in {(32,32), (64,64)}, Cout <= 32. */
+int wsis_mlp_head_coutp(int Cout);
+int wsis_mlp_head(const float *src, const int32_t *gather, int64_t n, int Cin, int H, int Cout, const float *w1t,
+                  const float *t1, const float *w2t, const float *b2, float *out, wsis_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------- */
 /* inter-superpoint affinity (edge attention) and random-walk label propagation                     */
 /* ---------------------------------------------------------------------------------------------- */

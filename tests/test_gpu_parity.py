@@ -874,3 +874,30 @@ def test_ecc_gru_fused_matches_module(W, orc, S, E, layernorm):
                                cell.weight_hh.detach().cpu().numpy(), cell.bias_ih.detach().cpu().numpy(),
                                cell.bias_hh.detach().cpu().numpy(), layernorm=layernorm)
         assert rel(o[:, 32 * r + 32:32 * r + 64], exp) < 2e-5
+
+
+@pytest.mark.parametrize("C,cout,n", [(32, 20, 70001), (64, 20, 3000), (64, 3, 3000), (64, 1, 1), (64, 7, 257), (32, 32, 129)])
+def test_fused_mlp_head_matches_torch(W, C, cout, n):
+    """csrc/heads.cu: Linear -> BatchNorm1d(eval) -> ReLU -> Linear (backbone_3D_WSIS.py:57-62, 71-104) in one kernel,
+    with and without the fused voxel -> point gather, against the torch modules."""
+    torch.manual_seed(C + cout)
+    head = torch.nn.Sequential(torch.nn.Linear(C, C), torch.nn.BatchNorm1d(C, eps=1e-4), torch.nn.ReLU(inplace=True),
+                               torch.nn.Linear(C, cout)).cuda().eval()
+    with torch.no_grad():
+        head[1].running_mean.uniform_(-0.5, 0.5)
+        head[1].running_var.uniform_(0.5, 2.0)
+        head[1].weight.uniform_(0.5, 1.5)
+        head[1].bias.uniform_(-0.5, 0.5)
+        x = torch.randn(n, C, device="cuda")
+        assert W.mlp_head_supported(head, x)
+        ref = head(x.clone())
+        assert rel(W.mlp_head(head, x).cpu().numpy(), ref.cpu().numpy()) < 1e-5
+        idx = torch.randint(0, n, (2 * n + 3,), device="cuda", dtype=torch.int32)
+        got = W.mlp_head(head, x, gather=idx)
+        assert rel(got.cpu().numpy(), ref[idx.long()].cpu().numpy()) < 1e-5
+        # parameter edits through load_state_dict are seen (cache epoch)
+        sd = {k: v.clone() for k, v in head.state_dict().items()}
+        sd["3.bias"] += 1.0
+        head.load_state_dict(sd)
+        W.invalidate_caches()
+        assert rel(W.mlp_head(head, x).cpu().numpy(), (ref + 1.0).cpu().numpy()) < 1e-5
