@@ -552,31 +552,29 @@ def run_train(args, rank, world, local_rank):
     t_end = time.time()
     t_e2e, _, io, ms_e2e = timed(step_e2e, args.steps, args.warmup)
 
-    # stage split of one step (CUDA events on the launching stream; outside the timed regions)
-    stages = None
-    if rank == 0:
-        from wsis_b200.train import loss_inputs
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-        flush.zero_()
-        step.opt.zero_grad()
-        evs[0].record()
-        with torch.enable_grad():
-            ret, _ = pipeline.forward_batch(net, dev[0])
-            evs[1].record()
-            loss, _ = step.loss(loss_inputs(ret, dev[0]), step.epoch)
-            evs[2].record()
-            loss.backward()
-        evs[3].record()
+    # stage split of one step (CUDA events on the launching stream; outside the timed regions).  EVERY rank runs it:
+    # the synchronised BatchNorm statistics and the gradient bucket are collectives.
+    from wsis_b200.train import loss_inputs
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    flush.zero_()
+    step.opt.zero_grad()
+    evs[0].record()
+    with torch.enable_grad():
+        ret, _ = pipeline.forward_batch(net, dev[0])
+        evs[1].record()
+        loss, _ = step.loss(loss_inputs(ret, dev[0]), step.epoch)
+        evs[2].record()
+        loss.backward()
+    evs[3].record()
     if world > 1:
         dist.all_reduce(step.opt.bucket.flat)
-    if rank == 0:
-        evs[4].record()
-        step.opt.step(grad_scale=1.0 / world)
-        evs[5].record()
-        torch.cuda.synchronize()
-        names = ["forward", "loss", "backward", "grad_allreduce", "adamw"]
-        stages = {n: round(evs[i].elapsed_time(evs[i + 1]), 3) for i, n in enumerate(names)}
-    launches_total = count_all_launches(lambda: step_resident(0)) if rank == 0 else None
+    evs[4].record()
+    step.opt.step(grad_scale=1.0 / world)
+    evs[5].record()
+    torch.cuda.synchronize()
+    names = ["forward", "loss", "backward", "grad_allreduce", "adamw"]
+    stages = {n: round(evs[i].elapsed_time(evs[i + 1]), 3) for i, n in enumerate(names)}
+    launches_total = count_all_launches(lambda: step_resident(0))       # a full step: all ranks (collectives inside)
     cpu = parity_obj = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         want = {}
