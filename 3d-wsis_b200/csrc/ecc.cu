@@ -41,7 +41,8 @@ __device__ __forceinline__ void layer_norm96(float &a, float &b, float &c, float
 __global__ void __launch_bounds__(256)
 ecc_gru_step_kernel(const float *__restrict__ h, const float *__restrict__ filters, const int64_t *__restrict__ src,
                     const int32_t *__restrict__ eorder, const int32_t *__restrict__ offsets, int64_t S, const float *__restrict__ params, int layernorm,
-                    float eps, float *__restrict__ h_out, float *__restrict__ cat_out, int64_t cat_stride) {
+                    float eps, float *__restrict__ h_out, float *__restrict__ cat_out, int64_t cat_stride,
+                    const float *__restrict__ msg) {
   __shared__ float sp[kEccParams];
   for (int i = threadIdx.x; i < kEccParams; i += blockDim.x) sp[i] = __ldg(params + i);
   __syncthreads();
@@ -51,6 +52,9 @@ ecc_gru_step_kernel(const float *__restrict__ h, const float *__restrict__ filte
   const int beg = __ldg(offsets + t), end = __ldg(offsets + t + 1);
   // ---- NNConv: mean of h[s]^T W_e over the in-edges ----
   float m = 0.f;
+  if (filters == nullptr) {                  // the messages were produced by ecc_umma.cu, one row per edge in CSR order
+    for (int j = beg; j < end; ++j) m += __ldg(msg + (int64_t)j * kF + lane);
+  } else
   for (int j = beg; j < end; ++j) {
     const int e = eorder != nullptr ? __ldg(eorder + j) : j;
     const int64_t s = __ldg(src + e);
@@ -110,7 +114,20 @@ int wsis_ecc_gru_step(const float *h, const float *filters, const int64_t *src, 
   if (S == 0) return 0;
   const int warps_per_block = 8;
   ecc_gru_step_kernel<<<(unsigned)ceil_div(S, warps_per_block), warps_per_block * 32, 0, as_stream(stream)>>>(
-      h, filters, src, eorder, offsets, S, params, layernorm, eps, h_out, cat_out, cat_stride);
+      h, filters, src, eorder, offsets, S, params, layernorm, eps, h_out, cat_out, cat_stride, nullptr);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_ecc_gru_step_msg(const float *h, const float *msg, const int32_t *offsets, int64_t S, const float *params,
+                          int layernorm, float eps, float *h_out, float *cat_out, int64_t cat_stride,
+                          wsis_stream_t stream) {
+  WSIS_CHECK(S >= 0 && S < ((int64_t)1 << 31), "ecc_gru_step_msg: S out of range");
+  WSIS_CHECK(h != h_out, "ecc_gru_step_msg: the state buffers must differ");
+  if (S == 0) return 0;
+  const int warps_per_block = 8;
+  ecc_gru_step_kernel<<<(unsigned)ceil_div(S, warps_per_block), warps_per_block * 32, 0, as_stream(stream)>>>(
+      h, nullptr, nullptr, nullptr, offsets, S, params, layernorm, eps, h_out, cat_out, cat_stride, msg);
   WSIS_LAUNCH_OK();
   return 0;
 }

@@ -238,12 +238,24 @@ class RNNGraphConvModule(nn.Module):
     def forward(self, hx):
         edgefeats = self._gci.get_buffers()[4]
         edge_index = self._gci.get_pyg_buffers()
-        weights = _seq(self._fnet, edgefeats)
         nc = hx.size(1)
-        assert hx.dim() == 2 and weights.dim() == 2 and weights.size(1) == nc * nc
         cell = self._cell
-        if (not torch.is_grad_enabled() and hx.is_cuda and hx.dtype == torch.float32 and nc == 32
-                and isinstance(cell, GRUCellEx) and cell._ingate and cell.bias):
+        fast = (not torch.is_grad_enabled() and hx.is_cuda and hx.dtype == torch.float32 and nc == 32
+                and isinstance(cell, GRUCellEx) and cell._ingate and cell.bias)
+        if fast and W.ECC_FUSED_FILTERS and W.ecc_fnet_supported(self._fnet) and edgefeats.dtype == torch.float32:
+            # inference: the [E,1024] filters are never materialised (csrc/ecc_umma.cu regenerates them on the tensor
+            # cores inside every step), one message kernel + one GRU kernel per step
+            key = tuple(p._version for p in cell.parameters()) + tuple(p.data_ptr() for p in cell.parameters()) + \
+                (W.cache_epoch(),)
+            if getattr(self, "_packed_key", None) != key:
+                self._packed_key, self._packed = key, W.pack_ecc_gru(cell)
+            tseg = W.SegmentIndex(edge_index[1], hx.shape[0])
+            return W.ecc_gru_fused(hx, self._fnet, edgefeats, edge_index[0], tseg, self._packed, self._nrepeats,
+                                   layernorm=cell._layernorm, eps=cell._modules['ini'].eps if cell._layernorm else 1e-5,
+                                   cat_all=self._cat_all)
+        weights = _seq(self._fnet, edgefeats)
+        assert hx.dim() == 2 and weights.dim() == 2 and weights.size(1) == nc * nc
+        if fast:
             # inference: one kernel per GRU step (message, gates, layer norms and the concatenation fused;
             # csrc/ecc.cu) instead of ~20 torch launches
             key = tuple(p._version for p in cell.parameters()) + tuple(p.data_ptr() for p in cell.parameters()) + \

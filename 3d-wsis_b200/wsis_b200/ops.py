@@ -21,6 +21,11 @@ from ._lib import lib
 _PRECISION = os.environ.get("WSIS_PRECISION", "fp32")
 
 
+# inference ECC-GRU: regenerate the edge filters on the tensor cores inside every step (csrc/ecc_umma.cu) instead of
+# materialising [E,1024] with library GEMMs and streaming it 7 times; False = the streaming kernel (csrc/ecc.cu)
+ECC_FUSED_FILTERS = os.environ.get("WSIS_ECC_FUSED", "1") != "0"
+
+
 def set_precision(p):
     global _PRECISION
     assert p in ("fp32", "bf16", "simt"), p
@@ -637,6 +642,80 @@ def ecc_gru(hx, filters, src, tseg, params, nrepeats, layernorm=True, eps=1e-5, 
         cat_ptr = ctypes.c_void_p(cat.data_ptr() + 4 * F * (r + 1)) if cat_all else None
         lib().call("wsis_ecc_gru_step", _ptr(h), _ptr(filters), _ptr(src), _ptr(tseg.order), _ptr(tseg.offsets), S,
                    _ptr(params), int(layernorm), float(eps), _ptr(out), cat_ptr, width, _stream())
+        h = out
+    return cat if cat_all else h
+
+
+def ecc_fnet_supported(fnet):
+    """Filter network of the 3D-WSIS ECC layer (graphnet.py:21-39 with widths 13-32-128-64-1024, BatchNorm after the
+    third Linear, eval mode): Linear, ReLU, Linear, ReLU, Linear, BatchNorm1d, ReLU, Linear."""
+    import torch.nn as nn
+    m = list(fnet._modules.values()) if hasattr(fnet, "_modules") else []
+    kinds = [nn.Linear, nn.ReLU, nn.Linear, nn.ReLU, nn.Linear, nn.BatchNorm1d, nn.ReLU, nn.Linear]
+    if len(m) != len(kinds) or not all(isinstance(a, k) for a, k in zip(m, kinds)):
+        return False
+    shapes = [(m[0].in_features, m[0].out_features), (m[2].in_features, m[2].out_features),
+              (m[4].in_features, m[4].out_features), (m[7].in_features, m[7].out_features)]
+    return shapes == [(13, 32), (32, 128), (128, 64), (64, 1024)] and not m[5].training and m[5].track_running_stats
+
+
+def pack_ecc_fnet(fnet):
+    """-> (edge-MLP parameter pack f32[wsis_ecc_edge_mlp_param_floats()], W4 operand image, b4 f32[1024] or None);
+    cached on the module per parameter version / cache epoch."""
+    m = list(fnet._modules.values())
+    ps = [p for mod in m for p in list(mod.parameters()) + list(mod.buffers())]
+    key = tuple((p._version, p.data_ptr()) for p in ps) + (_CACHE_EPOCH,)
+    cache = getattr(fnet, "_wsis_fnet", None)
+    if cache is None or cache[0] != key:
+        l1, l2, l3, bn, l4 = m[0], m[2], m[4], m[5], m[7]
+        with torch.no_grad():
+            inv = torch.rsqrt(bn.running_var.float() + bn.eps)
+            scale = (bn.weight.float() if bn.weight is not None else torch.ones_like(inv)) * inv
+            shift = (bn.bias.float() if bn.bias is not None else torch.zeros_like(inv)) - bn.running_mean.float() * scale
+
+            def bias(l):
+                return l.bias.float() if l.bias is not None else torch.zeros(l.out_features, device=l.weight.device)
+            params = torch.cat([l1.weight.float().t().reshape(-1), bias(l1), l2.weight.float().t().reshape(-1), bias(l2),
+                                (l3.weight.float() * scale.unsqueeze(1)).t().reshape(-1), bias(l3) * scale + shift]).contiguous()
+            assert params.numel() == lib().value("wsis_ecc_edge_mlp_param_floats")
+            w4 = l4.weight.detach().float().contiguous()
+            w4p = _bytes(lib().value("wsis_ecc_w4_bytes"), w4.device)
+            lib().call("wsis_ecc_pack_w4", _ptr(w4), _ptr(w4p), _stream())
+            b4 = l4.bias.detach().float().contiguous() if l4.bias is not None else None
+        cache = (key, params, w4p, b4)
+        fnet._wsis_fnet = cache
+    return cache[1:]
+
+
+def ecc_gru_fused(hx, fnet, edgefeats, src, tseg, params, nrepeats, layernorm=True, eps=1e-5, cat_all=True,
+                  edges_sorted=False):
+    """`nrepeats` ECC-GRU steps WITHOUT materialised edge filters (csrc/ecc_umma.cu): the filter network's hidden
+    layers run once per edge, the 64 -> 1024 filter layer is regenerated on the tensor cores inside every step.
+    hx f32[S,32]; edgefeats f32[E,13]; src int64[E]; tseg = SegmentIndex of the edge TARGETS; `edges_sorted`: the
+    edge arrays are already in target order (ecc/GraphConvInfo.py:50-76), so tseg.order is the identity."""
+    hx = _cuda(hx, "hx").contiguous()
+    edgefeats = _cuda(edgefeats, "edge features").contiguous()
+    src = src.contiguous()
+    S, F = hx.shape
+    E = src.shape[0]
+    assert F == 32 and hx.dtype == torch.float32 and edgefeats.shape == (E, 13) and tseg.S == S and tseg.n == E
+    mlp, w4p, b4 = pack_ecc_fnet(fnet)
+    dev = hx.device
+    eorder = None if edges_sorted else tseg.order
+    he = _bytes(lib().value("wsis_ecc_he_bytes", E), dev)
+    lib().call("wsis_ecc_edge_mlp", _ptr(edgefeats), _ptr(eorder), E, _ptr(mlp), _ptr(he), _stream())
+    msg = torch.empty((max(E, 1), F), dtype=torch.float32, device=dev)
+    width = F * (nrepeats + 1)
+    cat = torch.empty((S, width), dtype=torch.float32, device=dev) if cat_all else None
+    if cat_all:
+        cat[:, :F] = hx
+    h = hx
+    for r in range(nrepeats):
+        out = torch.empty_like(h)
+        lib().call("wsis_ecc_messages", _ptr(he), _ptr(w4p), _ptr(b4), _ptr(h), _ptr(src), _ptr(eorder), E, _ptr(msg), _stream())
+        cat_ptr = ctypes.c_void_p(cat.data_ptr() + 4 * F * (r + 1)) if cat_all else None
+        lib().call("wsis_ecc_gru_step_msg", _ptr(h), _ptr(msg), _ptr(tseg.offsets), S, _ptr(params), int(layernorm),
+                   float(eps), _ptr(out), cat_ptr, width, _stream())
         h = out
     return cat if cat_all else h
 

@@ -48,6 +48,72 @@ def to_device(batch, device="cuda", non_blocking=True):
     return out, nbytes
 
 
+class BatchStream(object):
+    """Iterates over collated HOST batches (pinned: pin_batch) and yields (device batch, bytes copied): the host -> device
+    copy of batch i+1 is issued on a copy stream while batch i is being computed on the current stream, the way the
+    reference's DataLoader(pin_memory=True) + .cuda(non_blocking) loop overlaps them (train_scannetv2.py:149-172).
+    Every batch is still copied exactly once; nothing is cached across iterations."""
+
+    def __init__(self, host_batches, device="cuda", depth=1):
+        self.host_batches, self.device, self.depth = host_batches, device, max(int(depth), 1)
+        self.copy_stream = torch.cuda.Stream()
+
+    def _issue(self, batch):
+        with torch.cuda.stream(self.copy_stream):
+            db, nb = to_device(batch, self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return db, nb, ev
+
+    def __iter__(self):
+        import collections
+        it = iter(self.host_batches)
+        q = collections.deque()
+        for b in it:
+            q.append(self._issue(b))
+            if len(q) > self.depth:
+                break
+        while q:
+            db, nb, ev = q.popleft()
+            nxt = next(it, None)
+            if nxt is not None:
+                q.append(self._issue(nxt))                      # overlaps the compute of `db`
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for v in db.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(cur)                        # allocated on the copy stream, consumed on `cur`
+            yield db, nb
+
+
+class ResultFetcher(object):
+    """Asynchronous device -> host read of a step's results into pinned buffers (stream-ordered, no host sync per
+    step); `wait()` blocks until everything fetched so far has landed."""
+
+    def __init__(self, keys=("edge_affinity", "sp_semantic_scores", "sp_discriminative_feats", "pred_sp_offset_vectors")):
+        self.keys, self.bufs, self.last = keys, {}, None
+
+    def fetch(self, ret):
+        out, nbytes = {}, 0
+        for k in self.keys:
+            t = ret[k]
+            buf = self.bufs.get(k)
+            if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+                buf = torch.empty((int(t.numel() * 1.25) + 16,), dtype=t.dtype, pin_memory=True)
+                self.bufs[k] = buf
+            view = buf[:t.numel()].view(t.shape)
+            view.copy_(t, non_blocking=True)
+            out[k] = view
+            nbytes += t.numel() * t.element_size()
+        self.last = torch.cuda.Event()
+        self.last.record()
+        return out, nbytes
+
+    def wait(self):
+        if self.last is not None:
+            self.last.synchronize()
+
+
 def forward_batch(model, dbatch, use_coords=True, mode=4, keep_unet_features=False):
     """Voxelization + UNet + pooling + affinity for one device-resident batch.  Returns (ret dict, aux dict)."""
     locs = dbatch["locs"]

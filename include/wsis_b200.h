@@ -261,6 +261,28 @@ int wsis_ecc_gru_step(const float *h, const float *filters, const int64_t *src, 
                       const float *params, int layernorm, float eps, float *h_out, float *cat_out, int64_t cat_stride,
                       wsis_stream_t stream);
 
+/* ECC-GRU without materialised edge filters (graphnet.py:21-39, spg_modules.py:152-185; csrc/ecc_umma.cu): the
+ * 32x32 filter of every edge, F_e = W4 . he_e + b4, is regenerated by the tensor cores inside every step and
+ * contracted with the source state on the spot, m_e = h[src(e)]^T F_e; [E,1024] never exists in memory.
+ *   wsis_ecc_edge_mlp: once per forward.  he = ReLU(BN(L3(ReLU(L2(ReLU(L1(edgefeats))))))) (widths 13-32-128-64) for the
+ *     edges in target-CSR order (edge j = eorder[j], eorder NULL = identity), written as the MMA's operand tiles into
+ *     he_packed (wsis_ecc_he_bytes(E) bytes).  params float[wsis_ecc_edge_mlp_param_floats()] =
+ *     W1^T[13][32] | b1[32] | W2^T[32][128] | b2[128] | (diag(bn_scale) W3)^T[128][64] | bn_scale*b3+bn_shift [64].
+ *   wsis_ecc_pack_w4: W4 float[1024][64] (the last Linear's weight) -> w4_packed (wsis_ecc_w4_bytes() bytes).
+ *   wsis_ecc_messages: one GRU step's messages msg float[E,32] (row j = edge eorder[j]); b4 float[1024] or NULL.
+ *   wsis_ecc_gru_step_msg: wsis_ecc_gru_step with the mean taken over the message rows [offsets[t], offsets[t+1]). */
+int64_t wsis_ecc_edge_mlp_param_floats(void);
+int64_t wsis_ecc_he_bytes(int64_t E);
+int64_t wsis_ecc_w4_bytes(void);
+int wsis_ecc_pack_w4(const float *w4, void *w4_packed, wsis_stream_t stream);
+int wsis_ecc_edge_mlp(const float *edgefeats, const int32_t *eorder, int64_t E, const float *params, void *he_packed,
+                      wsis_stream_t stream);
+int wsis_ecc_messages(const void *he_packed, const void *w4_packed, const float *b4, const float *h, const int64_t *src,
+                      const int32_t *eorder, int64_t E, float *msg, wsis_stream_t stream);
+int wsis_ecc_gru_step_msg(const float *h, const float *msg, const int32_t *offsets, int64_t S, const float *params,
+                          int layernorm, float eps, float *h_out, float *cat_out, int64_t cat_stride,
+                          wsis_stream_t stream);
+
 /* Random-walk label propagation (modules/datasets/scannetv2_dataset.py:664-735 + the dense fill at
  * train_scannetv2.py:565-570), float64 like the reference, exploiting that the transition matrix is
  * adjacency-masked and that only seed rows of T^(it+1) are read (:714-715).
