@@ -308,3 +308,221 @@ int wsis_adamw_step(float *p, const float *g, float *m, float *v, int64_t n, flo
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Point-level semantic loss (losses_3D_WSIS.py:52-64): cross entropy (mean over labelled points) + multi-class dice
+// on the softmax of the labelled points, forward and backward in two passes over the [N, C] scores instead of ~25
+// elementwise / reduction launches that each stream [N, C].
+//   fwd: per point lse, p = softmax; block partials of {ce, n, I_c = sum p_c [y=c], Q_c = sum p_c^2, T_c = #[y=c]}
+//   fin: loss = ce/n + mean_c (1 - (2 I_c + eps)/(Q_c + T_c + 1e-4 + eps)); coefficients a_c, b_c of dL/dp_c = a_c [y=c] + b_c p_c
+//   bwd: dlogit_k = g * { (p_k - [k=y])/n + p_k (gp_k - sum_j p_j gp_j) }, gp_j = a_j [y=j] + b_j p_j   (0 for ignored points)
+// ------------------------------------------------------------------------------------------------------------------
+namespace wsis {
+
+constexpr int kLossMaxC = 32;
+constexpr int kLossThreads = 256;
+
+template <int CP>   // CP = classes padded to a multiple of 4
+__device__ __forceinline__ void load_logits(const float *__restrict__ row, int C, float (&l)[CP]) {
+  if (C == CP) {
+#pragma unroll
+    for (int c4 = 0; c4 < CP / 4; ++c4) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + c4);
+      l[c4 * 4] = v.x, l[c4 * 4 + 1] = v.y, l[c4 * 4 + 2] = v.z, l[c4 * 4 + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CP; ++c) l[c] = c < C ? __ldg(row + c) : -INFINITY;
+  }
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kLossThreads)
+ce_dice_fwd_kernel(const float *__restrict__ scores, const int64_t *__restrict__ labels, int64_t N, int C, int ignore,
+                   float *__restrict__ partial /* [grid][2 + 3 CP] */) {
+  float ce = 0.f, cnt = 0.f, I[CP], Q[CP], T[CP];
+#pragma unroll
+  for (int c = 0; c < CP; ++c) I[c] = Q[c] = T[c] = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)__ldg(labels + i);
+    if (y == ignore) continue;
+    float l[CP];
+    load_logits<CP>(scores + i * C, C, l);
+    float mx = l[0];
+#pragma unroll
+    for (int c = 1; c < CP; ++c) mx = fmaxf(mx, l[c]);
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      l[c] = __expf(l[c] - mx);
+      se += l[c];
+    }
+    const float inv = 1.f / se;
+    cnt += 1.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      const float p = l[c] * inv;
+      Q[c] = fmaf(p, p, Q[c]);
+      if (c == y) {
+        I[c] += p;
+        T[c] += 1.f;
+        ce -= __logf(p);
+      }
+    }
+  }
+  __shared__ float s_red[kLossThreads / 32][2 + 3 * CP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  auto red = [&](float v, int slot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[w][slot] = v;
+  };
+  red(ce, 0);
+  red(cnt, 1);
+#pragma unroll
+  for (int c = 0; c < CP; ++c) {
+    red(I[c], 2 + c);
+    red(Q[c], 2 + CP + c);
+    red(T[c], 2 + 2 * CP + c);
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < 2 + 3 * CP; s += blockDim.x) {
+    float acc = 0.f;
+    for (int ww = 0; ww < kLossThreads / 32; ++ww) acc += s_red[ww][s];
+    partial[(int64_t)blockIdx.x * (2 + 3 * CP) + s] = acc;
+  }
+}
+
+// out[0] = loss, out[1] = n, out[2 + c] = a_c, out[2 + CP + c] = b_c (floats)
+__global__ void ce_dice_finalize_kernel(const float *__restrict__ partial, int nblocks, int C, int CP, int dice,
+                                        float *__restrict__ out) {
+  __shared__ double s[2 + 3 * kLossMaxC];
+  const int slots = 2 + 3 * CP;
+  for (int i = threadIdx.x; i < slots; i += blockDim.x) {
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += (double)partial[(int64_t)b * slots + i];
+    s[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double n = s[1];
+    double loss = n > 0 ? s[0] / n : 0.0 / 0.0;            // CrossEntropyLoss over zero labelled points is NaN in torch too
+    if (dice) {
+      double d = 0.0;
+      for (int c = 0; c < C; ++c) {
+        const double I = s[2 + c], Q = s[2 + CP + c], T = s[2 + 2 * CP + c];
+        const double num = 2.0 * I + 1e-5, den = Q + T + 1e-4 + 1e-5;
+        d += 1.0 - num / den;
+        out[2 + c] = (float)(-2.0 / (C * den));
+        out[2 + CP + c] = (float)(2.0 * num / (C * den * den));
+      }
+      loss += d / C;
+    } else {
+      for (int c = 0; c < CP; ++c) out[2 + c] = out[2 + CP + c] = 0.f;
+    }
+    out[0] = (float)loss;
+    out[1] = (float)n;
+  }
+}
+
+template <int CP>
+__global__ void __launch_bounds__(kLossThreads)
+ce_dice_bwd_kernel(const float *__restrict__ scores, const int64_t *__restrict__ labels, int64_t N, int C, int ignore,
+                   const float *__restrict__ fin, const float *__restrict__ gout, float *__restrict__ dscores) {
+  __shared__ float s_a[CP], s_b[CP];
+  if (threadIdx.x < CP) {
+    s_a[threadIdx.x] = fin[2 + threadIdx.x];
+    s_b[threadIdx.x] = fin[2 + CP + threadIdx.x];
+  }
+  __syncthreads();
+  const float g = gout ? __ldg(gout) : 1.f, invn = 1.f / fin[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)__ldg(labels + i);
+    float l[CP];
+    if (y == ignore) {
+#pragma unroll
+      for (int c = 0; c < CP; ++c) l[c] = 0.f;
+    } else {
+      load_logits<CP>(scores + i * C, C, l);
+      float mx = l[0];
+#pragma unroll
+      for (int c = 1; c < CP; ++c) mx = fmaxf(mx, l[c]);
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        l[c] = __expf(l[c] - mx);
+        se += l[c];
+      }
+      const float inv = 1.f / se;
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        l[c] *= inv;                                          // p_c
+        dot = fmaf(l[c], (c == y ? s_a[c] : 0.f) + s_b[c] * l[c], dot);
+      }
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        const float gp = (c == y ? s_a[c] : 0.f) + s_b[c] * l[c];
+        l[c] = g * ((l[c] - (c == y ? 1.f : 0.f)) * invn + l[c] * (gp - dot));
+      }
+    }
+    float *o = dscores + i * C;
+    if (C == CP) {
+#pragma unroll
+      for (int c4 = 0; c4 < CP / 4; ++c4)
+        reinterpret_cast<float4 *>(o)[c4] = make_float4(l[c4 * 4], l[c4 * 4 + 1], l[c4 * 4 + 2], l[c4 * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < C) o[c] = l[c];
+    }
+  }
+}
+
+static int loss_grid(int64_t N) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(N, kLossThreads), (int64_t)sm_count() * 4));
+}
+
+}  // namespace wsis
+
+extern "C" {
+
+int64_t wsis_ce_dice_ws_bytes(int64_t N, int C) {
+  int cp = (C + 3) / 4 * 4;
+  return (int64_t)wsis::loss_grid(N) * (2 + 3 * cp) * sizeof(float);
+}
+
+int wsis_ce_dice_fwd(const float *scores, const int64_t *labels, int64_t N, int C, int ignore_label, int dice, void *ws,
+                     float *fin, wsis_stream_t stream) {
+  using namespace wsis;
+  WSIS_CHECK(C >= 1 && C <= kLossMaxC, "ce_dice: 1 <= classes <= 32");
+  cudaStream_t st = as_stream(stream);
+  const int cp = (C + 3) / 4 * 4, grid = loss_grid(N);
+  switch (cp) {
+#define WSIS_CE(CPV) case CPV: ce_dice_fwd_kernel<CPV><<<grid, kLossThreads, 0, st>>>(scores, labels, N, C, ignore_label, (float *)ws); break;
+    WSIS_CE(4) WSIS_CE(8) WSIS_CE(12) WSIS_CE(16) WSIS_CE(20) WSIS_CE(24) WSIS_CE(28) WSIS_CE(32)
+#undef WSIS_CE
+  }
+  WSIS_LAUNCH_OK();
+  ce_dice_finalize_kernel<<<1, 128, 0, st>>>((const float *)ws, grid, C, cp, dice, fin);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_ce_dice_bwd(const float *scores, const int64_t *labels, int64_t N, int C, int ignore_label, const float *fin,
+                     const float *grad_out, float *dscores, wsis_stream_t stream) {
+  using namespace wsis;
+  WSIS_CHECK(C >= 1 && C <= kLossMaxC, "ce_dice: 1 <= classes <= 32");
+  if (N == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int cp = (C + 3) / 4 * 4, grid = loss_grid(N);
+  switch (cp) {
+#define WSIS_CE(CPV) case CPV: ce_dice_bwd_kernel<CPV><<<grid, kLossThreads, 0, st>>>(scores, labels, N, C, ignore_label, fin, grad_out, dscores); break;
+    WSIS_CE(4) WSIS_CE(8) WSIS_CE(12) WSIS_CE(16) WSIS_CE(20) WSIS_CE(24) WSIS_CE(28) WSIS_CE(32)
+#undef WSIS_CE
+  }
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

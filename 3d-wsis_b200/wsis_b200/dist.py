@@ -88,7 +88,19 @@ class GradBucket:
                 p.grad = view
             off += n
 
+    def check_aliasing(self):
+        """Every parameter's .grad must still be its view of the flat buffer: `optimizer.zero_grad(set_to_none=True)`
+        (the torch default) drops the views, autograd then allocates fresh gradients and the all-reduce of the bucket
+        would silently synchronise nothing.  Use `bucket.zero()` instead of `optimizer.zero_grad()`."""
+        off = 0
+        for p, n in zip(self.params, self.sizes):
+            if p.grad is not None and p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
+                raise RuntimeError("GradBucket: a parameter's .grad no longer aliases the flat bucket (was "
+                                   "optimizer.zero_grad(set_to_none=True) called?); call bucket.zero() instead")
+            off += n
+
     def allreduce(self, async_op=False):
+        self.check_aliasing()
         _, world_size = world()
         if world_size == 1:
             return None

@@ -54,9 +54,11 @@ class BatchStream(object):
     reference's DataLoader(pin_memory=True) + .cuda(non_blocking) loop overlaps them (train_scannetv2.py:149-172).
     Every batch is still copied exactly once; nothing is cached across iterations."""
 
-    def __init__(self, host_batches, device="cuda", depth=1):
+    def __init__(self, host_batches, device="cuda", depth=1, copy_stream=None):
         self.host_batches, self.device, self.depth = host_batches, device, max(int(depth), 1)
-        self.copy_stream = torch.cuda.Stream()
+        # a long-lived loader passes its own copy stream: the caching allocator keeps one pool per stream, so a fresh
+        # stream starts with cudaMalloc calls
+        self.copy_stream = copy_stream if copy_stream is not None else torch.cuda.Stream()
 
     def _issue(self, batch):
         with torch.cuda.stream(self.copy_stream):

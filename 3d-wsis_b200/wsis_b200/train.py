@@ -169,6 +169,50 @@ def run_sequential(seq, x):
     return x
 
 
+class _CEDice(torch.autograd.Function):
+    """CrossEntropyLoss(ignore_index) [+ multi-class dice on the softmax of the labelled rows] (losses_3D_WSIS.py:
+    52-64, 72-74) as two passes over the scores (csrc/train.cu ce_dice_*)."""
+
+    @staticmethod
+    def forward(ctx, scores, labels, ignore_label, dice):
+        scores = scores.contiguous()
+        labels = labels.contiguous()
+        N, C = scores.shape
+        cp = (C + 3) // 4 * 4
+        fin = torch.empty((2 + 2 * cp,), dtype=torch.float32, device=scores.device)
+        ws = _bytes(lib().value("wsis_ce_dice_ws_bytes", N, C), scores.device)
+        lib().call("wsis_ce_dice_fwd", _ptr(scores), _ptr(labels), N, C, int(ignore_label), int(dice), _ptr(ws), _ptr(fin),
+                   _stream())
+        ctx.save_for_backward(scores, labels, fin)
+        ctx.ignore = int(ignore_label)
+        return fin[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        scores, labels, fin = ctx.saved_tensors
+        N, C = scores.shape
+        d = torch.empty_like(scores)
+        g = g.contiguous().float()
+        lib().call("wsis_ce_dice_bwd", _ptr(scores), _ptr(labels), N, C, ctx.ignore, _ptr(fin), _ptr(g), _ptr(d), _stream())
+        return d, None, None, None
+
+
+def ce_dice_loss(scores, labels, ignore_label=-100, dice=True):
+    """The fused kernel for float32 CUDA scores with at most 32 classes; the torch formulation otherwise."""
+    if scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2 and scores.shape[1] <= 32 \
+            and labels.dtype == torch.int64 and FUSED:
+        return _CEDice.apply(scores, labels, ignore_label, bool(dice))
+    loss = F.cross_entropy(scores, labels, ignore_index=ignore_label)
+    if dice:
+        keep = labels != ignore_label
+        C = scores.shape[1]
+        p = F.softmax(scores, dim=-1) * keep.unsqueeze(1)
+        onehot = F.one_hot(labels.clamp(min=0), C) * keep.unsqueeze(1)
+        d = (2 * (p * onehot).sum(0) + 1e-5) / ((p * p).sum(0) + onehot.sum(0) + 1e-4 + 1e-5)
+        loss = loss + (1.0 - d).mean()
+    return loss
+
+
 # ---------------------------------------------------------------------------------------------------------
 # loss (modules/model/losses_3D_WSIS.py) -- one vectorised formulation for the whole batch, no per-scene Python loop
 # ---------------------------------------------------------------------------------------------------------
@@ -192,19 +236,13 @@ class MultiTaskLoss(nn.Module):
         out = {}
         semantic_labels, instance_labels = inp['point_labels']
         scores = inp["semantic_scores"]
-        loss = F.cross_entropy(scores, semantic_labels, ignore_index=self.ignore_label)          # :56
-        if self.semantic_dice:                                                                    # :57-63
-            keep = semantic_labels != self.ignore_label
-            p = F.softmax(scores, dim=-1) * keep.unsqueeze(1)
-            onehot = F.one_hot(semantic_labels.clamp(min=0), self.classes) * keep.unsqueeze(1)
-            dice = (2 * (p * onehot).sum(0) + 1e-5) / ((p * p).sum(0) + onehot.sum(0) + 1e-4 + 1e-5)
-            loss = loss + (1.0 - dice).mean()
+        loss = ce_dice_loss(scores, semantic_labels, self.ignore_label, self.semantic_dice)      # :56-63
         out["semantic_loss"] = loss
         if epoch > self.joint_training_epoch:
             sp_sem, sp_ins = inp['superpoint_labels']
             valid = (sp_ins != self.ignore_label) & (sp_sem != self.ignore_label)                # :69
             nvalid = valid.sum()
-            out["superpoint_semantic_loss"] = F.cross_entropy(inp['sp_semantic'], sp_sem, ignore_index=self.ignore_label)
+            out["superpoint_semantic_loss"] = ce_dice_loss(inp['sp_semantic'], sp_sem, self.ignore_label, False)   # :72-74
             loss = loss + out["superpoint_semantic_loss"]
             if self.supervise_sp_offset:                                                          # :77-93
                 pred, gt = inp['sp_offset_vector']

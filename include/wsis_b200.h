@@ -336,6 +336,17 @@ int wsis_bn_bwd_reduce(const float *x, const float *da, int64_t N, int C, const 
                        double *sums, float *dgamma, float *dbeta, wsis_stream_t stream);
 int wsis_bn_bwd_apply(const float *x, const float *da, int64_t N, int C, const float *stat, int relu,
                       const double *sums, const double *count, const float *extra, float *dx, wsis_stream_t stream);
+/* Semantic loss of losses_3D_WSIS.py:52-64 (and :72-74 without dice): CrossEntropyLoss(ignore_index) + multi-class dice
+ * on the softmax of the labelled rows, forward and backward in two passes over scores float[N,C] (C <= 32).
+ *   wsis_ce_dice_fwd: fin float[2 + 2*cp] (cp = C rounded up to 4): fin[0] = loss, fin[1] = #labelled rows, then the
+ *                     per-class coefficients the backward needs.  ws: wsis_ce_dice_ws_bytes(N, C).
+ *   wsis_ce_dice_bwd: dscores float[N,C] = d loss / d scores * (*grad_out, or 1 when NULL); ignored rows get zeros. */
+int64_t wsis_ce_dice_ws_bytes(int64_t N, int C);
+int wsis_ce_dice_fwd(const float *scores, const int64_t *labels, int64_t N, int C, int ignore_label, int dice, void *ws,
+                     float *fin, wsis_stream_t stream);
+int wsis_ce_dice_bwd(const float *scores, const int64_t *labels, int64_t N, int C, int ignore_label, const float *fin,
+                     const float *grad_out, float *dscores, wsis_stream_t stream);
+
 /* torch.optim.AdamW (train_scannetv2.py:93-94) over flat buffers, `step` counts from 1.  The gradient is first
  * multiplied by grad_scale (1/world for a sum-all-reduced bucket) and elements [clamp_begin, clamp_end) are
  * clamped to [-1, 1] (the ECC gradient clamp, train_scannetv2.py:246-249). */

@@ -243,3 +243,27 @@ def test_train_step_updates_parameters_and_loss_decreases(T):
     with torch.no_grad():
         ret, _ = pipeline.forward_batch(net, batch)
     assert torch.isfinite(ret["semantic_scores"]).all()
+
+
+@pytest.mark.parametrize("N,C,dice,frac", [(50000, 20, True, 0.3), (3001, 20, False, 0.5), (777, 7, True, 1.0), (64, 32, True, 0.1)])
+def test_fused_ce_dice_kernel_matches_torch(T, N, C, dice, frac):
+    """csrc/train.cu ce_dice_fwd/bwd against the torch formulation of losses_3D_WSIS.py:52-64 (CrossEntropyLoss with
+    ignore_index + dice on the labelled rows): value and gradient, scaled by an upstream gradient."""
+    torch.manual_seed(N)
+    scores = (torch.randn(N, C, device="cuda") * 3).requires_grad_(True)
+    labels = torch.randint(0, C, (N,), device="cuda")
+    labels[torch.rand(N, device="cuda") > frac] = -100
+    labels[0] = 1
+    a = T.ce_dice_loss(scores, labels, -100, dice)
+    (a * 1.7).backward()
+    ga = scores.grad.clone()
+    scores.grad = None
+    T.FUSED = False
+    try:
+        b = T.ce_dice_loss(scores, labels, -100, dice)
+    finally:
+        T.FUSED = True
+    (b * 1.7).backward()
+    assert abs(a.item() - b.item()) < 1e-5 * abs(b.item())
+    assert rel(ga.cpu(), scores.grad.cpu()) < 2e-5
+    assert float(ga[labels == -100].abs().max()) == 0.0 if bool((labels == -100).any()) else True
