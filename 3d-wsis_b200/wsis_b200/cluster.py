@@ -10,8 +10,10 @@ group (O(S*N) memory traffic, ~3000 x 150k per scene); here everything is done o
 (point count, centre, voxel keys in one stable sort by superpoint) and the N-point masks are produced once, at the
 end, from a superpoint -> instance table.
 
-This is host control logic over a graph of a few thousand nodes; it launches no kernel.  `neighbors[s]` is the list
-the reference gets from `graph.neighbors(vertex=s, mode='all')` (igraph; ascending vertex ids).
+`clustering_in_graph` is the host restatement (numpy; what the golden vectors of the reference's own function pin);
+`clustering_in_graph_device` runs the same algorithm on the GPU (csrc/cluster.cu: one warp walks the graph, the
+point-sized work is parallel kernels) and returns device tensors.  `neighbors[s]` is the list the reference gets from
+`graph.neighbors(vertex=s, mode='all')` (igraph; ascending vertex ids).
 """
 import collections
 from math import sqrt
@@ -145,3 +147,63 @@ def clustering_in_graph(xyz_origin, superpoint, neighbors, sp_semantic_pred, pre
     masks = (point_inst[None, :] == np.arange(len(primaries))[:, None]).astype(int) if primaries \
         else np.zeros((0, len(superpoint)), dtype=int)
     return np.array(conf), np.array(label_id), masks
+
+
+def neighbors_csr_device(edges, num_superpoints):
+    """(nbr_off int32[S+1], nbr int32[...]) on the device from an int64[E,2] CUDA edge list: both directions, duplicates
+    removed, ascending neighbour id per vertex (= neighbors_from_edges)."""
+    import torch
+    both = torch.cat([edges, edges.flip(1)]).long()
+    key = torch.unique(both[:, 0] * num_superpoints + both[:, 1])          # sorted by (vertex, neighbour)
+    src, nbr = torch.div(key, num_superpoints, rounding_mode="floor"), key % num_superpoints
+    off = torch.zeros(num_superpoints + 1, dtype=torch.int64, device=edges.device)
+    off[1:] = torch.cumsum(torch.bincount(src, minlength=num_superpoints), 0)
+    return off.int().contiguous(), nbr.int().contiguous()
+
+
+def clustering_in_graph_device(xyz_origin, superpoint, nbr_csr, sp_semantic_pred, pred_sp_offset_vectors, pred_sp_occupancy,
+                               pred_sp_ins_size, num_superpoints=None, semantic_ind2label=SEMANTIC_IND2LABEL,
+                               valid_labels=INSTANCE_VALID_LABELS, voxel_scale=50, sp_index=None):
+    """Device version of clustering_in_graph for one scene.  CUDA tensors in: xyz_origin f32[N,3], superpoint int64[N],
+    nbr_csr = neighbors_csr_device(...), sp_semantic_pred int[S], offsets f32[S,3], occupancy f32[S], size f32[S].
+    Returns (conf float64[I], label_id int32[I], point_inst int32[N], inst_of_sp int32[S]) as CUDA tensors; the
+    reference's dense masks are `dense_masks(point_inst, I)`.  One host sync (the number of instances)."""
+    import ctypes
+
+    import torch
+
+    from . import ops as W
+    from ._lib import lib
+    xyz = xyz_origin.contiguous().float()
+    superpoint = superpoint.contiguous().long()
+    N = xyz.shape[0]
+    S = int(num_superpoints) if num_superpoints is not None else int(sp_semantic_pred.shape[0])
+    dev = xyz.device
+    seg = sp_index if sp_index is not None else W.SegmentIndex(superpoint, S)
+    centre = (W.segment_reduce(xyz, seg, "mean") + pred_sp_offset_vectors.float()).contiguous()       # :295-305
+    count = (seg.offsets[1:] - seg.offsets[:-1]).int().contiguous()
+    n_class = len(semantic_ind2label)
+    valid = torch.tensor([1 if int(x) in set(int(v) for v in valid_labels) else 0 for x in semantic_ind2label],
+                         dtype=torch.int32, device=dev)
+    ind2label = torch.tensor([int(x) for x in semantic_ind2label], dtype=torch.int32, device=dev)
+    sem = sp_semantic_pred.int().contiguous()
+    occ, size = pred_sp_occupancy.float().contiguous(), pred_sp_ins_size.float().contiguous()
+    nbr_off, nbr = nbr_csr
+    ws = torch.empty(int(lib().value("wsis_cluster_ws_bytes", N, S)) + 256, dtype=torch.uint8, device=dev)
+    conf = torch.empty((S,), dtype=torch.float64, device=dev)
+    label_id = torch.empty((S,), dtype=torch.int32, device=dev)
+    inst_of_sp = torch.empty((S,), dtype=torch.int32, device=dev)
+    point_inst = torch.empty((N,), dtype=torch.int32, device=dev)
+    n_inst = torch.zeros((1,), dtype=torch.int32, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    lib().call("wsis_cluster", p(xyz), p(superpoint), N, S, p(nbr_off), p(nbr), p(sem), p(centre), p(count), p(occ), p(size),
+               p(valid), p(ind2label), n_class, float(voxel_scale), p(ws), p(conf), p(label_id), p(inst_of_sp),
+               p(point_inst), p(n_inst), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    n = int(n_inst.item())
+    return conf[:n], label_id[:n], point_inst, inst_of_sp
+
+
+def dense_masks(point_inst, n_instances):
+    """int[I, N] masks of the reference (test_scannetv2.py:449-457) from the point -> instance table."""
+    import torch
+    return (point_inst.unsqueeze(0) == torch.arange(n_instances, device=point_inst.device, dtype=point_inst.dtype).unsqueeze(1)).long()

@@ -283,6 +283,21 @@ int wsis_ecc_gru_step_msg(const float *h, const float *msg, const int32_t *offse
                           int layernorm, float eps, float *h_out, float *cat_out, int64_t cat_stride,
                           wsis_stream_t stream);
 
+/* Instance clustering on the superpoint graph of ONE scene (test_scannetv2.py:281-455 clustering_in_graph), on the
+ * device.  xyz float[N,3] = xyz_origin; superpoint int64[N] in [0,S); (nbr_off int32[S+1], nbr int32[...]) = adjacency
+ * lists in ascending neighbour id (igraph neighbors(mode='all')); sem int32[S] = argmax class per superpoint; centre
+ * float[S,3] = superpoint centre + predicted offset (:305); count int32[S] = points per superpoint; occ / size float[S] =
+ * pred_sp_occupancy / pred_sp_ins_size; class_valid int32[n_class] (1 = instance class), ind2label int32[n_class].
+ * Outputs: conf double[<=S], label_id int32[<=S], inst_of_sp int32[S] (-1 = none), point_inst int32[N] (the dense
+ * masks of the reference are point_inst[None,:] == arange(I)[:,None]), n_inst int32[1] (device).
+ * ws: wsis_cluster_ws_bytes(N, S).  S < 65536. */
+int64_t wsis_cluster_ws_bytes(int64_t N, int64_t S);
+int wsis_cluster(const float *xyz, const int64_t *superpoint, int64_t N, int64_t S, const int32_t *nbr_off,
+                 const int32_t *nbr, const int32_t *sem, const float *centre, const int32_t *count, const float *occ,
+                 const float *size, const int32_t *class_valid, const int32_t *ind2label, int n_class, float voxel_scale,
+                 void *ws, double *conf, int32_t *label_id, int32_t *inst_of_sp, int32_t *point_inst, int32_t *n_inst,
+                 wsis_stream_t stream);
+
 /* Random-walk label propagation (modules/datasets/scannetv2_dataset.py:664-735 + the dense fill at
  * train_scannetv2.py:565-570), float64 like the reference, exploiting that the transition matrix is
  * adjacency-masked and that only seed rows of T^(it+1) are read (:714-715).

@@ -943,3 +943,60 @@ def test_final_instance_masks_identical_to_reference_cpu_path(W, seed):
     assert mask_a.shape == mask_b.shape and np.array_equal(mask_a, mask_b)
     assert np.array_equal(lab_a, lab_b)
     assert np.allclose(conf_a, conf_b, rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("name", ["cluster_scene0", "cluster_scene1"])
+def test_device_clustering_matches_reference_golden(W, name):
+    """csrc/cluster.cu (one warp walks the superpoint graph, point-sized work in parallel kernels) against the outputs of
+    the reference's OWN clustering_in_graph (test_scannetv2.py:281-455, executed by tests/golden/make_golden_cluster.py):
+    identical instance masks and labels, confidences to 1e-6 (the group means are summed in member order instead of
+    numpy's pairwise float32 order)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    import make_golden_cluster as mg
+    from wsis_b200 import cluster
+    gold = np.load(os.path.join(root, "tests", "golden", name + ".npz"))
+    case, nbrs = mg.make_case(int(gold["seed"]), int(gold["n_points"]))
+    S = len(case["sem"])
+    edges = np.array([(s, n) for s in range(S) for n in nbrs[s]], dtype=np.int64).reshape(-1, 2)
+    csr = cluster.neighbors_csr_device(cu(edges), S)
+    off = csr[0].cpu().numpy()
+    assert all(csr[1][off[s]:off[s + 1]].cpu().tolist() == list(nbrs[s]) for s in range(0, S, 97))
+    conf, label, point_inst, inst_of_sp = cluster.clustering_in_graph_device(
+        cu(case["xyz"]), cu(case["superpoint"].astype(np.int64)), csr, cu(case["sem"].astype(np.int64)), cu(case["off"]),
+        cu(case["occ"]), cu(case["size"]), num_superpoints=S)
+    I = conf.shape[0]
+    masks = cluster.dense_masks(point_inst, I).cpu().numpy()
+    assert np.array_equal(np.packbits(masks.astype(bool), axis=1), gold["masks"])
+    assert np.array_equal(label.cpu().numpy(), gold["label_id"])
+    assert np.allclose(conf.cpu().numpy(), gold["conf"], rtol=1e-6, atol=0)
+
+
+def test_device_clustering_on_network_outputs_equals_host(W):
+    """Network (CUDA path) -> argmax -> instance clustering entirely on the device, against the host restatement fed
+    with the same network outputs: identical masks and labels on a full-size scene."""
+    from wsis_b200 import cluster, pipeline, synthetic
+    sc = synthetic.make_scene(2003, n_points=60000)
+    batch = synthetic.collate([sc])
+    net = pipeline.build_network(seed=123, device="cuda").eval()
+    db = pipeline.to_device(batch)[0]
+    with torch.no_grad():
+        ret, aux = pipeline.forward_batch(net, db)
+    S = sc["num_superpoints"]
+    sem = ret["sp_semantic_scores"].max(1)[1]
+    csr = cluster.neighbors_csr_device(cu(sc["edges"]), S)
+    conf, label, point_inst, _ = cluster.clustering_in_graph_device(
+        cu(sc["xyz"]), db["superpoint"], csr, sem, ret["pred_sp_offset_vectors"], ret["pred_sp_occupancy"],
+        ret["pred_sp_ins_size"], num_superpoints=S)
+    nbrs = cluster.neighbors_from_edges(sc["edges"], S)
+    hconf, hlabel, hmasks = cluster.clustering_in_graph(sc["xyz"], sc["superpoint"], nbrs, sem.cpu().numpy(),
+                                                        ret["pred_sp_offset_vectors"].cpu().numpy(),
+                                                        ret["pred_sp_occupancy"].cpu().numpy(),
+                                                        ret["pred_sp_ins_size"].cpu().numpy())
+    I = conf.shape[0]
+    assert I == len(hconf) and I > 10
+    host_inst = np.where(hmasks.any(0), hmasks.argmax(0), -1)
+    assert np.array_equal(point_inst.cpu().numpy(), host_inst)
+    assert np.array_equal(label.cpu().numpy(), hlabel)
+    assert np.allclose(conf.cpu().numpy(), hconf, rtol=1e-5, atol=0)
