@@ -233,6 +233,125 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Synchronised statistics: combine + all-reduce over NVLink peer memory + finalize in ONE kernel (one block).
+//
+// torch.nn.SyncBatchNorm (train_scannetv2.py:736) all-reduces 2C+1 numbers per BatchNorm and direction: with NCCL that
+// is ~110 BatchNorms x 2 latency-bound collectives of a few hundred bytes per step.  Here every rank owns a SYMMETRIC
+// buffer (torch symmetric memory: the same allocation mapped into every peer), laid out as
+//     double data[2][world][slot]  |  uint32 flag[2][world]            (2 = parity of the call's sequence number)
+// and the block that has just combined the local column sums (a) stores them into slot [parity][rank] of EVERY peer's
+// buffer with plain NVLink stores, (b) fences and release-stores the call's sequence number into flag [parity][rank] of
+// every peer, (c) acquire-spins until its own flags hold the sequence number for every rank, (d) adds the world's
+// contributions in rank order (bitwise the same result on every rank) and goes on to the finalize step.  Two parities
+// are enough: a peer cannot start call k+2 before this rank has contributed to k+1, i.e. finished reading call k.
+// A wait that does not complete within ~2 s is a protocol error (ranks out of step): trap instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------------------------
+struct PeerComm {
+  const unsigned long long *peers;   // device array [world] of the peers' buffer base addresses (own included)
+  int world, rank, slot;             // slot = doubles per contribution (>= 2C+1)
+  unsigned int seq;                  // 1, 2, 3, ... identical on every rank
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// s_sums[0..n) (shared) holds this rank's contribution on entry and the world's sum on exit
+__device__ void peer_allreduce(double *s_sums, int n, const PeerComm &pc) {
+  if (pc.world <= 1) return;
+  const int par = (int)(pc.seq & 1u);
+  const size_t flag_off = (size_t)2 * pc.world * pc.slot;           // in doubles
+  for (int r = 0; r < pc.world; ++r) {
+    double *dst = reinterpret_cast<double *>(pc.peers[r]) + ((size_t)par * pc.world + pc.rank) * pc.slot;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = s_sums[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < pc.world) {
+    unsigned int *pf = reinterpret_cast<unsigned int *>(reinterpret_cast<double *>(pc.peers[threadIdx.x]) + flag_off) +
+                       par * pc.world + pc.rank;
+    st_release_sys(pf, pc.seq);
+    const unsigned int *mf = reinterpret_cast<const unsigned int *>(reinterpret_cast<double *>(pc.peers[pc.rank]) + flag_off) +
+                             par * pc.world + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mf) != pc.seq) {
+      if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const double *mine = reinterpret_cast<const double *>(pc.peers[pc.rank]) + (size_t)par * pc.world * pc.slot;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < pc.world; ++r) acc += __ldcg(mine + (size_t)r * pc.slot + i);
+    s_sums[i] = acc;
+  }
+  __syncthreads();
+}
+
+// one block of 1024 threads: local combine (warp per column) -> peer all-reduce -> forward: finalize / backward: sums out
+__global__ void __launch_bounds__(1024)
+bn_sync_kernel(const float *__restrict__ partial, int nblocks, int C, double count, int forward, PeerComm pc,
+               double *__restrict__ sums_out, float *__restrict__ dgamma, float *__restrict__ dbeta,
+               const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
+               float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ stat) {
+  extern __shared__ double s_sums[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = warp; i < 2 * C; i += nw) {
+    const int c = i < C ? i : i - C;
+    double acc = 0.0;
+    for (int b = lane; b < nblocks; b += 32) {
+      const float *pb = partial + (int64_t)b * (3 * C + 1);
+      if (forward) {
+        const double nb = (double)pb[3 * C], p = (double)pb[2 * C + c], s1 = (double)pb[c], s2 = (double)pb[C + c];
+        acc += i < C ? s1 + nb * p : s2 + 2.0 * p * s1 + nb * p * p;
+      } else {
+        acc += (double)pb[i];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      s_sums[i] = acc;
+      if (!forward) {                         // parameter gradients are the LOCAL sums (the gradient bucket is all-reduced later)
+        if (dbeta && i < C) dbeta[i] = (float)acc;
+        if (dgamma && i >= C) dgamma[i - C] = (float)acc;
+      }
+    }
+  }
+  if (threadIdx.x == 0 && forward) s_sums[2 * C] = count;
+  __syncthreads();
+  const int n = forward ? 2 * C + 1 : 2 * C;
+  peer_allreduce(s_sums, n, pc);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sums_out[i] = s_sums[i];
+  if (forward && stat) {
+    const double tot = s_sums[2 * C];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double mean = s_sums[c] / tot;
+      double var = s_sums[C + c] / tot - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      float invstd = (float)(1.0 / sqrt(var + (double)eps));
+      float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+      float scale = g * invstd;
+      stat[c] = (float)mean;
+      stat[C + c] = invstd;
+      stat[2 * C + c] = scale;
+      stat[3 * C + c] = b - (float)mean * scale;
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      if (running_var) {
+        double unbiased = tot > 1.0 ? var * tot / (tot - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+}
+
 static int bn_grid(int64_t N, int C, int *rpp_out) {
   int tpr = (C + 3) / 4;
   int rpp = kBnThreads / tpr;
@@ -259,6 +378,42 @@ int wsis_bn_stats(const float *x, int64_t N, int C, void *ws, double *sums, wsis
   bn_colsum_kernel<0><<<blocks, kBnThreads, sizeof(float) * rpp * 2 * C, st>>>(x, nullptr, N, C, nullptr, 0, (float *)ws);
   WSIS_LAUNCH_OK();
   bn_combine_kernel<<<(2 * C + 7) / 8, 256, 0, st>>>((const float *)ws, blocks, C, (double)N, 1, sums, nullptr, nullptr, x, N, rpp);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+// Forward statistics + (world > 1: all-reduce over peer memory) + finalize as partial kernel + ONE block.
+// peers: device uint64[world] of the symmetric buffers' base addresses (NULL when world == 1); seq counts the
+// synchronised calls (same on all ranks, starts at 1); slot = doubles per contribution (>= 2C+1).
+int wsis_bn_forward_sync(const float *x, int64_t N, int C, void *ws, double *sums, const float *gamma, const float *beta,
+                         float eps, float momentum, float *running_mean, float *running_var, float *stat,
+                         const void *peers, int world, int rank, int64_t seq, int slot, wsis_stream_t stream) {
+  WSIS_CHECK(C >= 1 && C <= 1024, "bn_forward_sync: 1 <= C <= 1024");
+  WSIS_CHECK(world == 1 || (peers != nullptr && slot >= 2 * C + 1 && seq >= 1), "bn_forward_sync: bad peer arguments");
+  cudaStream_t st = as_stream(stream);
+  int rpp, blocks = bn_grid(N, C, &rpp);
+  bn_colsum_kernel<0><<<blocks, kBnThreads, sizeof(float) * rpp * 2 * C, st>>>(x, nullptr, N, C, nullptr, 0, (float *)ws);
+  WSIS_LAUNCH_OK();
+  PeerComm pc{(const unsigned long long *)peers, world, rank, slot, (unsigned int)seq};
+  bn_sync_kernel<<<1, 1024, sizeof(double) * (2 * C + 1), st>>>((const float *)ws, blocks, C, (double)N, 1, pc, sums, nullptr,
+                                                                nullptr, gamma, beta, eps, momentum, running_mean,
+                                                                running_var, stat);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_bn_bwd_reduce_sync(const float *x, const float *da, int64_t N, int C, const float *stat, int relu, void *ws,
+                            double *sums, float *dgamma, float *dbeta, const void *peers, int world, int rank,
+                            int64_t seq, int slot, wsis_stream_t stream) {
+  WSIS_CHECK(C >= 1 && C <= 1024, "bn_bwd_reduce_sync: 1 <= C <= 1024");
+  WSIS_CHECK(world == 1 || (peers != nullptr && slot >= 2 * C + 1 && seq >= 1), "bn_bwd_reduce_sync: bad peer arguments");
+  cudaStream_t st = as_stream(stream);
+  int rpp, blocks = bn_grid(N, C, &rpp);
+  bn_colsum_kernel<1><<<blocks, kBnThreads, sizeof(float) * rpp * 2 * C, st>>>(x, da, N, C, stat, relu, (float *)ws);
+  WSIS_LAUNCH_OK();
+  PeerComm pc{(const unsigned long long *)peers, world, rank, slot, (unsigned int)seq};
+  bn_sync_kernel<<<1, 1024, sizeof(double) * (2 * C + 1), st>>>((const float *)ws, blocks, C, 0.0, 0, pc, sums, dgamma, dbeta,
+                                                                nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr);
   WSIS_LAUNCH_OK();
   return 0;
 }

@@ -63,8 +63,9 @@ class _SuperpointTable(object):
 
 def clustering_in_graph(xyz_origin, superpoint, neighbors, sp_semantic_pred, pred_sp_offset_vectors, pred_sp_occupancy,
                         pred_sp_ins_size, semantic_ind2label=SEMANTIC_IND2LABEL,
-                        valid_labels=INSTANCE_VALID_LABELS, voxel_scale=50):
-    """-> (conf float[I], label_id int[I], masks int[I, N]); same contract as test_scannetv2.py:281-455."""
+                        valid_labels=INSTANCE_VALID_LABELS, voxel_scale=50, dense=True):
+    """-> (conf float[I], label_id int[I], masks int[I, N]); same contract as test_scannetv2.py:281-455.
+    dense=False returns the point -> instance table int64[N] (-1 = none) instead of the I x N masks."""
     xyz_origin = np.asarray(xyz_origin)
     superpoint = np.asarray(superpoint)
     assert len(xyz_origin) == len(superpoint)
@@ -144,6 +145,8 @@ def clustering_in_graph(xyz_origin, superpoint, neighbors, sp_semantic_pred, pre
         label_id.append(semantic_ind2label[prim["classLabel"]])
         inst_of_sp[np.array(prim["group_sp_list"])] = i
     point_inst = inst_of_sp[superpoint]
+    if not dense:
+        return np.array(conf), np.array(label_id), point_inst
     masks = (point_inst[None, :] == np.arange(len(primaries))[:, None]).astype(int) if primaries \
         else np.zeros((0, len(superpoint)), dtype=int)
     return np.array(conf), np.array(label_id), masks

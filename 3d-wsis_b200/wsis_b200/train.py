@@ -32,8 +32,58 @@ SYNC_BN = True
 FUSED = True
 
 
+# "peer": the statistics all-reduce happens INSIDE the combine kernel through NVLink peer stores into torch symmetric
+# memory (csrc/train.cu bn_sync_kernel); "nccl": dist.all_reduce of the fp64 sums between two kernels.  "peer" falls back
+# to "nccl" when symmetric memory cannot be set up (no P2P access, gloo group).
+SYNC_BN_TRANSPORT = "peer"
+
+
 def _sync():
     return SYNC_BN and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class _PeerSync(object):
+    """Symmetric buffer + sequence counter for the in-kernel statistics all-reduce (one per process)."""
+    SLOT = 2 * 1024 + 8            # doubles per contribution: up to C = 1024 channels
+
+    def __init__(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        n = 2 * self.world * self.SLOT + 2 * self.world          # data + flags (uint32 pairs packed into doubles' space)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(n, dtype=torch.float64, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.seq = 0
+
+    def next_seq(self):
+        self.seq += 1
+        if self.seq >= (1 << 31):
+            raise RuntimeError("wsis_b200: statistics sequence counter overflow")
+        return self.seq
+
+
+_PEER = None
+_PEER_FAILED = False
+
+
+def _peer():
+    """The process's _PeerSync, or None when the peer transport is off / unavailable."""
+    global _PEER, _PEER_FAILED
+    if SYNC_BN_TRANSPORT != "peer" or _PEER_FAILED or not _sync() or dist.get_backend() != "nccl":
+        return None
+    if _PEER is None:
+        try:
+            _PEER = _PeerSync()
+        except Exception as e:  # noqa: BLE001  (no symmetric memory on this build / no P2P): use NCCL
+            import warnings
+            warnings.warn("wsis_b200: symmetric-memory statistics all-reduce unavailable (%s); using NCCL" % (e,))
+            _PEER_FAILED = True
+            return None
+    return _PEER
 
 
 def bn_forward_stats(x, bn):
@@ -43,14 +93,26 @@ def bn_forward_stats(x, bn):
     dev = x.device
     sums = torch.empty((2 * C + 1,), dtype=torch.float64, device=dev)
     ws = _bytes(lib().value("wsis_bn_ws_bytes", N, C), dev)
-    lib().call("wsis_bn_stats", _ptr(x), N, C, _ptr(ws), _ptr(sums), _stream())
-    if _sync():
-        dist.all_reduce(sums)
     stat = torch.empty((4, C), dtype=torch.float32, device=dev)
     track = bn.track_running_stats and bn.running_mean is not None
     momentum = 0.0 if bn.momentum is None else float(bn.momentum)
     if track and bn.momentum is None:      # cumulative moving average
         momentum = 1.0 / float(bn.num_batches_tracked.item() + 1)
+    peer = _peer()
+    if peer is not None or not _sync():
+        # one launch pair: column sums, then ONE block that combines, all-reduces over NVLink peer memory (world > 1)
+        # and finalizes
+        lib().call("wsis_bn_forward_sync", _ptr(x), N, C, _ptr(ws), _ptr(sums),
+                   _ptr(bn.weight.detach() if bn.weight is not None else None),
+                   _ptr(bn.bias.detach() if bn.bias is not None else None), float(bn.eps), momentum,
+                   _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None, _ptr(stat),
+                   _ptr(peer.peers) if peer else None, peer.world if peer else 1, peer.rank if peer else 0,
+                   peer.next_seq() if peer else 1, peer.SLOT if peer else 0, _stream())
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return stat, sums
+    lib().call("wsis_bn_stats", _ptr(x), N, C, _ptr(ws), _ptr(sums), _stream())
+    dist.all_reduce(sums)
     lib().call("wsis_bn_finalize", _ptr(sums), C, _ptr(bn.weight.detach() if bn.weight is not None else None),
                _ptr(bn.bias.detach() if bn.bias is not None else None), float(bn.eps), momentum,
                _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None, _ptr(stat), _stream())
@@ -68,10 +130,15 @@ def bn_backward(x, da, stat, sums_fwd, relu, want_affine=True):
     dgamma = torch.empty((C,), dtype=torch.float32, device=dev) if want_affine else None
     dbeta = torch.empty((C,), dtype=torch.float32, device=dev) if want_affine else None
     ws = _bytes(lib().value("wsis_bn_ws_bytes", N, C), dev)
-    lib().call("wsis_bn_bwd_reduce", _ptr(x), _ptr(da), N, C, _ptr(stat), int(relu), _ptr(ws), _ptr(sums), _ptr(dgamma),
-               _ptr(dbeta), _stream())
-    if _sync():
-        dist.all_reduce(sums)
+    peer = _peer()
+    if peer is not None:
+        lib().call("wsis_bn_bwd_reduce_sync", _ptr(x), _ptr(da), N, C, _ptr(stat), int(relu), _ptr(ws), _ptr(sums),
+                   _ptr(dgamma), _ptr(dbeta), _ptr(peer.peers), peer.world, peer.rank, peer.next_seq(), peer.SLOT, _stream())
+    else:
+        lib().call("wsis_bn_bwd_reduce", _ptr(x), _ptr(da), N, C, _ptr(stat), int(relu), _ptr(ws), _ptr(sums), _ptr(dgamma),
+                   _ptr(dbeta), _stream())
+        if _sync():
+            dist.all_reduce(sums)
     dx = torch.empty_like(x)
     count = sums_fwd[2 * C:]
     lib().call("wsis_bn_bwd_apply", _ptr(x), _ptr(da), N, C, _ptr(stat), int(relu), _ptr(sums), _ptr(count), None,

@@ -270,12 +270,12 @@ def conv_roofline(net, dbatch, pipeline, W, steps, peaks):
     # `ncu --set full` capture of this kernel on this layer shape, and `traffic_source` says so; null when the capture
     # is of another shape
     traffic, traffic_source = None, None
-    prof = os.path.join(ROOT, "profiles", "r02_ncu_conv_umma_v4.json")
+    prof = os.path.join(ROOT, "profiles", "r02_ncu_conv_umma_l2.json")
     if os.path.exists(prof):
         pj = json.load(open(prof))
         if list(pj.get("cin_cout_K_rows", [])) == list(shp):
             traffic = pj.get("dram_bytes_per_launch")
-            traffic_source = "profiles/r02_ncu_conv_umma_v4.json (ncu --set full of one launch of this layer shape, " \
+            traffic_source = "profiles/r02_ncu_conv_umma_l2.json (ncu --set full of one launch of this layer shape, " \
                              "not measured in this run)"
     ach_all = bsum / tsum / 1e9
     return {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -344,6 +344,21 @@ int wsis_conv_wgrad_umma(const float *src, const int32_t *map, const int32_t *or
  *                       `count` points at the (global) row count, i.e. element 2C of the forward sums.
  * ws: wsis_bn_ws_bytes(N, C).  Reductions are two-stage in a fixed order (deterministic). */
 int64_t wsis_bn_ws_bytes(int64_t N, int C);
+/* Synchronised statistics with the collective INSIDE the kernel (torch.nn.SyncBatchNorm, train_scannetv2.py:736):
+ * the block that combines the local column sums stores them into every peer's symmetric buffer over NVLink, signals
+ * with a release-store of the call's sequence number, acquire-waits for all ranks, adds the contributions in rank
+ * order and (forward) finalizes -- one kernel instead of combine + NCCL all-reduce + finalize.
+ *   peers: device uint64[world] = base address of every rank's symmetric buffer as mapped in THIS process (own
+ *          included); each buffer holds double data[2][world][slot] followed by uint32 flag[2][world], zero-filled
+ *          before the first call.  seq = 1, 2, 3, ... (the same on every rank); slot >= 2C+1.  world == 1: no peers.
+ *   wsis_bn_forward_sync    = wsis_bn_stats (+ all-reduce) + wsis_bn_finalize;  sums double[2C+1] also written.
+ *   wsis_bn_bwd_reduce_sync = wsis_bn_bwd_reduce (+ all-reduce of sums; dgamma / dbeta stay local). */
+int wsis_bn_forward_sync(const float *x, int64_t N, int C, void *ws, double *sums, const float *gamma, const float *beta,
+                         float eps, float momentum, float *running_mean, float *running_var, float *stat,
+                         const void *peers, int world, int rank, int64_t seq, int slot, wsis_stream_t stream);
+int wsis_bn_bwd_reduce_sync(const float *x, const float *da, int64_t N, int C, const float *stat, int relu, void *ws,
+                            double *sums, float *dgamma, float *dbeta, const void *peers, int world, int rank,
+                            int64_t seq, int slot, wsis_stream_t stream);
 int wsis_bn_stats(const float *x, int64_t N, int C, void *ws, double *sums, wsis_stream_t stream);
 int wsis_bn_finalize(const double *sums, int C, const float *gamma, const float *beta, float eps, float momentum,
                      float *running_mean, float *running_var, float *stat, wsis_stream_t stream);

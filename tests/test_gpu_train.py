@@ -267,3 +267,21 @@ def test_fused_ce_dice_kernel_matches_torch(T, N, C, dice, frac):
     assert abs(a.item() - b.item()) < 1e-5 * abs(b.item())
     assert rel(ga.cpu(), scores.grad.cpu()) < 2e-5
     assert float(ga[labels == -100].abs().max()) == 0.0 if bool((labels == -100).any()) else True
+
+
+def test_in_kernel_syncbn_allreduce_two_gpus():
+    """csrc/train.cu bn_sync_kernel (combine + all-reduce over NVLink peer memory + finalize in one kernel) on 2 GPUs under
+    torchrun: equal to the NCCL transport (1e-6) and to torch.nn.SyncBatchNorm (3e-5), statistics bitwise identical on
+    every rank.  Needs two devices; the single-GPU boxes skip it."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29611", os.path.join(root, "tools", "sync_bn_check.py")],
+                       capture_output=True, text=True, timeout=300)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and line, (r.stdout[-1500:], r.stderr[-1500:])
+    assert json.loads(line[-1])["ok"]
