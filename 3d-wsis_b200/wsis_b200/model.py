@@ -403,6 +403,10 @@ class Network(nn.Module):
         output_feats = None
         if fused:
             p2v = input_map if input_map.dtype == torch.int32 else input_map.int()
+        elif torch.is_grad_enabled() and output.features.is_cuda and output.features.dtype == torch.float32:
+            from . import train as T                                                  # training: own gather kernel + CSR backward
+            p2v = input_map if input_map.dtype == torch.int32 else input_map.int()
+            output_feats = T.gather_rows(output.features, p2v)                        # :179 voxel -> point
         else:
             output_feats = output.features[input_map.long()]                          # :179 voxel -> point
         if fused and W.mlp_head_supported(self.linear, output.features):
@@ -424,6 +428,11 @@ class Network(nn.Module):
                 embeddings = W.segment_reduce(output.features, seg, "mean", gather=p2v)
             else:
                 embeddings = W.segment_reduce(output_feats, seg, "mean")
+        elif torch.is_grad_enabled() and output_feats.is_cuda and output_feats.dtype == torch.float32 \
+                and (extra_data.get("sp_index") is not None or extra_data.get("num_superpoints") is not None):
+            from . import train as T
+            seg = extra_data.get("sp_index") or W.SegmentIndex(superpoint, int(extra_data["num_superpoints"]))
+            embeddings = T.segment_mean(output_feats, seg)                            # :188, no host sync, no atomics
         else:
             embeddings = _scatter_torch(output_feats, superpoint, "mean")
 

@@ -15,6 +15,7 @@ What is different from running the reference's modules under autograd:
     parameter buffer (`wsis_adamw_step`).
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -35,7 +36,7 @@ FUSED = True
 # "peer": the statistics all-reduce happens INSIDE the combine kernel through NVLink peer stores into torch symmetric
 # memory (csrc/train.cu bn_sync_kernel); "nccl": dist.all_reduce of the fp64 sums between two kernels.  "peer" falls back
 # to "nccl" when symmetric memory cannot be set up (no P2P access, gloo group).
-SYNC_BN_TRANSPORT = "peer"
+SYNC_BN_TRANSPORT = os.environ.get("WSIS_SYNC_BN_TRANSPORT", "peer")
 
 
 def _sync():
@@ -166,6 +167,57 @@ class _BNReLU(torch.autograd.Function):
 
 def batch_norm_train(x, bn, relu):
     return _BNReLU.apply(x, bn.weight, bn.bias, bn, bool(relu))
+
+
+class _GatherRows(torch.autograd.Function):
+    """out[i] = src[idx[i]] (voxel -> point gather, backbone_3D_WSIS.py:179) with the backward as a segmented sum over
+    the CSR of idx (one warp per source row, fixed order, no atomics) instead of torch's index_put accumulate."""
+
+    @staticmethod
+    def forward(ctx, src, idx32):
+        ctx.save_for_backward(idx32)
+        ctx.n_src = src.shape[0]
+        return W.gather_rows(src, idx32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx32,) = ctx.saved_tensors
+        seg = getattr(idx32, "_wsis_seg", None)
+        if seg is None or seg.S != ctx.n_src:
+            seg = W.SegmentIndex(idx32.long(), ctx.n_src)
+            try:
+                idx32._wsis_seg = seg
+            except Exception:  # noqa: BLE001
+                pass
+        return W.segment_reduce(g.contiguous(), seg, "sum"), None
+
+
+class _SegmentMean(torch.autograd.Function):
+    """out[s] = mean of the rows of segment s (superpoint pooling, backbone_3D_WSIS.py:188); backward
+    dsrc[i] = dout[ids[i]] / count[ids[i]] as one row gather."""
+
+    @staticmethod
+    def forward(ctx, src, seg):
+        ctx.seg = seg
+        return W.segment_reduce(src.contiguous(), seg, "mean")
+
+    @staticmethod
+    def backward(ctx, g):
+        seg = ctx.seg
+        cnt = (seg.offsets[1:] - seg.offsets[:-1]).clamp(min=1).to(g.dtype).unsqueeze(1)
+        ids32 = getattr(seg, "_ids32", None)
+        if ids32 is None:
+            ids32 = seg.ids.int()
+            seg._ids32 = ids32
+        return W.gather_rows((g / cnt).contiguous(), ids32), None
+
+
+def gather_rows(src, idx32):
+    return _GatherRows.apply(src, idx32)
+
+
+def segment_mean(src, seg):
+    return _SegmentMean.apply(src, seg)
 
 
 class _BNReLUConv(torch.autograd.Function):

@@ -45,7 +45,7 @@ for C, N in ((32, 5000 + 777 * rank), (64, 20000 + 13 * rank), (224, 900 + rank)
         y.backward(g)
         outs[transport] = [y.detach(), bn.running_mean.clone(), bn.running_var.clone(), xi.grad.clone(), bn.weight.grad.clone(),
                            bn.bias.grad.clone()]
-    assert T._peer() is not None or T._PEER_FAILED, "peer transport was never initialised"
+    assert T._PEER is not None or T._PEER_FAILED, "peer transport was never initialised"
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))  # noqa: E731
     case = {"C": C, "N_rank": N, "peer_vs_nccl": max(rel(a, b) for a, b in zip(outs["peer"], outs["nccl"])),
             "peer_vs_torch_syncbn": max(rel(a, b) for a, b in zip(outs["peer"], outs["torch"]))}
