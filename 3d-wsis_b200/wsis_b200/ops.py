@@ -168,6 +168,18 @@ class Rulebook:
         self._tiles = {}
 
     def pairs(self):
+        # The reference-format tensors carry a strong reference to this rulebook (`pairs._wsis_rulebook`, so that the
+        # rulebook lives as long as indice_dict holds the pairs); the way back is WEAK: a strong one would make every
+        # rulebook of every step (pairs [K,2,N] = 117 MB at level 1, tile records, maps) a reference cycle that only the
+        # cyclic collector frees -- in training that showed up as GBs of dead rulebooks and 100-380 ms allocator stalls.
+        cached = self._pairs
+        if cached is not None and not isinstance(cached, tuple):
+            cached = tuple(r() for r in cached)
+            if any(t is None for t in cached):
+                cached = None
+        if cached is not None:
+            return cached
+        self._pairs = None
         if self._pairs is None:
             dev = self.nbr_in.device
             N, K = self.n_in, self.K
@@ -180,7 +192,9 @@ class Rulebook:
                            _stream())
             else:
                 num.zero_()
-            self._pairs = (pairs, num)
+            import weakref
+            self._pairs = [weakref.ref(pairs), weakref.ref(num)]
+            return pairs, num
         return self._pairs
 
     # (map, flip) for: y[dst] = sum_k x[map[dst,k]] W[k]
@@ -310,7 +324,8 @@ def rulebook_from_pairs(pairs, num, n_in, n_out, subm):
         nbr_out = torch.full((n_out, K), -1, dtype=torch.int32, device=dev)
         lib().call("wsis_nbr_from_pairs", _ptr(pairs), _ptr(num), stride, K, 1, _ptr(nbr_out), _stream())
     rb = Rulebook("subm" if subm else "conv", K, n_in, n_out, nbr_in, nbr_out, None)
-    rb._pairs = (pairs, num)
+    import weakref
+    rb._pairs = [weakref.ref(pairs), weakref.ref(num)]     # weak: the caller's pairs tensor points back at `rb`
     return rb
 
 

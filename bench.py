@@ -591,18 +591,11 @@ def run_train(args, rank, world, local_rank):
             total = float(t.item())
         return total, W.launch_count() - l0, extra, per_step
 
-    # A training step issues ~2300 launches and builds an autograd graph of a few thousand Python objects: a cyclic-GC
-    # generation-2 pass landing inside a step showed up as single 100-380 ms outlier steps (70-75 ms otherwise).  The
-    # collector is run once here and then kept off the timed loops (the reference counts still free everything).
-    import gc
-    gc.collect()
-    gc.disable()
     clocks.wait_ready()
     t_begin = time.time()
     t_res, launches, _, ms_res = timed(step_resident, args.steps, args.warmup)
     t_end = time.time()
     t_e2e, _, io, ms_e2e = timed(step_e2e, args.steps, args.warmup)
-    gc.enable()
 
     # stage split of one step (CUDA events on the launching stream; outside the timed regions).  EVERY rank runs it:
     # the synchronised BatchNorm statistics and the gradient bucket are collectives.
