@@ -301,12 +301,16 @@ bn_sync_kernel(const float *__restrict__ partial, int nblocks, int C, double cou
                double *__restrict__ sums_out, float *__restrict__ dgamma, float *__restrict__ dbeta,
                const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
                float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ stat) {
-  extern __shared__ double s_sums[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i = warp; i < 2 * C; i += nw) {
+  extern __shared__ double s_sums[];          // [2C+1] sums, then [slices][2C] scratch
+  // thread (slice, column): consecutive threads read consecutive columns of one partial row (coalesced); a column's
+  // blocks are split over `slices` threads and added in slice order (fixed order: deterministic)
+  const int ncol = 2 * C, slices = max(1, (int)blockDim.x / ncol);
+  double *s_part = s_sums + (2 * C + 2);
+  const int i = threadIdx.x % ncol, sl = threadIdx.x / ncol;
+  if (sl < slices) {
     const int c = i < C ? i : i - C;
     double acc = 0.0;
-    for (int b = lane; b < nblocks; b += 32) {
+    for (int b = sl; b < nblocks; b += slices) {
       const float *pb = partial + (int64_t)b * (3 * C + 1);
       if (forward) {
         const double nb = (double)pb[3 * C], p = (double)pb[2 * C + c], s1 = (double)pb[c], s2 = (double)pb[C + c];
@@ -315,14 +319,16 @@ bn_sync_kernel(const float *__restrict__ partial, int nblocks, int C, double cou
         acc += (double)pb[i];
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      s_sums[i] = acc;
-      if (!forward) {                         // parameter gradients are the LOCAL sums (the gradient bucket is all-reduced later)
-        if (dbeta && i < C) dbeta[i] = (float)acc;
-        if (dgamma && i >= C) dgamma[i - C] = (float)acc;
-      }
+    s_part[sl * ncol + i] = acc;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < ncol; j += blockDim.x) {
+    double acc = 0.0;
+    for (int s2 = 0; s2 < slices; ++s2) acc += s_part[s2 * ncol + j];
+    s_sums[j] = acc;
+    if (!forward) {                           // parameter gradients are the LOCAL sums (the gradient bucket is all-reduced later)
+      if (dbeta && j < C) dbeta[j] = (float)acc;
+      if (dgamma && j >= C) dgamma[j - C] = (float)acc;
     }
   }
   if (threadIdx.x == 0 && forward) s_sums[2 * C] = count;
@@ -356,7 +362,7 @@ static int bn_grid(int64_t N, int C, int *rpp_out) {
   int tpr = (C + 3) / 4;
   int rpp = kBnThreads / tpr;
   *rpp_out = rpp;
-  int64_t blocks = std::min<int64_t>(std::min<int64_t>(ceil_div(N, (int64_t)rpp * 4), (int64_t)sm_count() * 4), 1024);
+  int64_t blocks = std::min<int64_t>(std::min<int64_t>(ceil_div(N, (int64_t)rpp * 4), (int64_t)sm_count() * 2), 1024);
   return (int)std::max<int64_t>(blocks, 1);
 }
 
@@ -388,14 +394,14 @@ int wsis_bn_stats(const float *x, int64_t N, int C, void *ws, double *sums, wsis
 int wsis_bn_forward_sync(const float *x, int64_t N, int C, void *ws, double *sums, const float *gamma, const float *beta,
                          float eps, float momentum, float *running_mean, float *running_var, float *stat,
                          const void *peers, int world, int rank, int64_t seq, int slot, wsis_stream_t stream) {
-  WSIS_CHECK(C >= 1 && C <= 1024, "bn_forward_sync: 1 <= C <= 1024");
+  WSIS_CHECK(C >= 1 && C <= 512, "bn_forward_sync: 1 <= C <= 512");
   WSIS_CHECK(world == 1 || (peers != nullptr && slot >= 2 * C + 1 && seq >= 1), "bn_forward_sync: bad peer arguments");
   cudaStream_t st = as_stream(stream);
   int rpp, blocks = bn_grid(N, C, &rpp);
   bn_colsum_kernel<0><<<blocks, kBnThreads, sizeof(float) * rpp * 2 * C, st>>>(x, nullptr, N, C, nullptr, 0, (float *)ws);
   WSIS_LAUNCH_OK();
   PeerComm pc{(const unsigned long long *)peers, world, rank, slot, (unsigned int)seq};
-  bn_sync_kernel<<<1, 1024, sizeof(double) * (2 * C + 1), st>>>((const float *)ws, blocks, C, (double)N, 1, pc, sums, nullptr,
+  bn_sync_kernel<<<1, 1024, sizeof(double) * (2 * C + 2 + 1024 + 2 * C), st>>>((const float *)ws, blocks, C, (double)N, 1, pc, sums, nullptr,
                                                                 nullptr, gamma, beta, eps, momentum, running_mean,
                                                                 running_var, stat);
   WSIS_LAUNCH_OK();
@@ -405,14 +411,14 @@ int wsis_bn_forward_sync(const float *x, int64_t N, int C, void *ws, double *sum
 int wsis_bn_bwd_reduce_sync(const float *x, const float *da, int64_t N, int C, const float *stat, int relu, void *ws,
                             double *sums, float *dgamma, float *dbeta, const void *peers, int world, int rank,
                             int64_t seq, int slot, wsis_stream_t stream) {
-  WSIS_CHECK(C >= 1 && C <= 1024, "bn_bwd_reduce_sync: 1 <= C <= 1024");
+  WSIS_CHECK(C >= 1 && C <= 512, "bn_bwd_reduce_sync: 1 <= C <= 512");
   WSIS_CHECK(world == 1 || (peers != nullptr && slot >= 2 * C + 1 && seq >= 1), "bn_bwd_reduce_sync: bad peer arguments");
   cudaStream_t st = as_stream(stream);
   int rpp, blocks = bn_grid(N, C, &rpp);
   bn_colsum_kernel<1><<<blocks, kBnThreads, sizeof(float) * rpp * 2 * C, st>>>(x, da, N, C, stat, relu, (float *)ws);
   WSIS_LAUNCH_OK();
   PeerComm pc{(const unsigned long long *)peers, world, rank, slot, (unsigned int)seq};
-  bn_sync_kernel<<<1, 1024, sizeof(double) * (2 * C + 1), st>>>((const float *)ws, blocks, C, 0.0, 0, pc, sums, dgamma, dbeta,
+  bn_sync_kernel<<<1, 1024, sizeof(double) * (2 * C + 2 + 1024 + 2 * C), st>>>((const float *)ws, blocks, C, 0.0, 0, pc, sums, dgamma, dbeta,
                                                                 nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr);
   WSIS_LAUNCH_OK();
   return 0;

@@ -100,7 +100,7 @@ def bn_forward_stats(x, bn):
     if track and bn.momentum is None:      # cumulative moving average
         momentum = 1.0 / float(bn.num_batches_tracked.item() + 1)
     peer = _peer()
-    if peer is not None or not _sync():
+    if (peer is not None or not _sync()) and C <= 512:
         # one launch pair: column sums, then ONE block that combines, all-reduces over NVLink peer memory (world > 1)
         # and finalizes
         lib().call("wsis_bn_forward_sync", _ptr(x), N, C, _ptr(ws), _ptr(sums),
@@ -113,7 +113,8 @@ def bn_forward_stats(x, bn):
             bn.num_batches_tracked.add_(1)
         return stat, sums
     lib().call("wsis_bn_stats", _ptr(x), N, C, _ptr(ws), _ptr(sums), _stream())
-    dist.all_reduce(sums)
+    if _sync():
+        dist.all_reduce(sums)
     lib().call("wsis_bn_finalize", _ptr(sums), C, _ptr(bn.weight.detach() if bn.weight is not None else None),
                _ptr(bn.bias.detach() if bn.bias is not None else None), float(bn.eps), momentum,
                _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None, _ptr(stat), _stream())
@@ -131,7 +132,7 @@ def bn_backward(x, da, stat, sums_fwd, relu, want_affine=True):
     dgamma = torch.empty((C,), dtype=torch.float32, device=dev) if want_affine else None
     dbeta = torch.empty((C,), dtype=torch.float32, device=dev) if want_affine else None
     ws = _bytes(lib().value("wsis_bn_ws_bytes", N, C), dev)
-    peer = _peer()
+    peer = _peer() if C <= 512 else None
     if peer is not None:
         lib().call("wsis_bn_bwd_reduce_sync", _ptr(x), _ptr(da), N, C, _ptr(stat), int(relu), _ptr(ws), _ptr(sums),
                    _ptr(dgamma), _ptr(dbeta), _ptr(peer.peers), peer.world, peer.rank, peer.next_seq(), peer.SLOT, _stream())
