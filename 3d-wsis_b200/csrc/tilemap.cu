@@ -256,8 +256,12 @@ int64_t wsis_tile_record_stride(int K) { return rec_stride_bytes(K); }
 int64_t wsis_tile_unique_stride(int K) { return (int64_t)kTile * K; }
 
 static int tile_table_slots(int K) {
+  // A tile has at most 128 K distinct source rows (every entry a different row: random maps); a surface patch has
+  // ~200.  The table is sized for the worst case at a load factor <= 0.89 (K = 27: 4096 slots, 32 KB for table + first
+  // entries) rather than <= 0.5: halving it takes the kernel from 2 to 4 resident CTAs per SM, and the linear probe is
+  // only long in the adversarial case.
   int ht = 256;
-  while (ht < 2 * kTile * K) ht <<= 1;
+  while (ht < kTile * K + kTile * K / 8) ht <<= 1;
   return ht;
 }
 

@@ -52,40 +52,62 @@ class BatchStream(object):
     """Iterates over collated HOST batches (pinned: pin_batch) and yields (device batch, bytes copied): the host -> device
     copy of batch i+1 is issued on a copy stream while batch i is being computed on the current stream, the way the
     reference's DataLoader(pin_memory=True) + .cuda(non_blocking) loop overlaps them (train_scannetv2.py:149-172).
-    Every batch is still copied exactly once; nothing is cached across iterations."""
+    Every batch is still copied exactly once; nothing is cached across iterations.
 
-    def __init__(self, host_batches, device="cuda", depth=1, copy_stream=None):
+    The device side is `depth + 1` sets of persistent staging buffers (grown on demand), so the two streams never meet
+    in the caching allocator: set k is overwritten only after the compute stream has finished the batch that used it
+    (an event recorded when the consumer asks for the next batch)."""
+
+    def __init__(self, host_batches, device="cuda", depth=1, copy_stream=None, staging=None):
         self.host_batches, self.device, self.depth = host_batches, device, max(int(depth), 1)
-        # a long-lived loader passes its own copy stream: the caching allocator keeps one pool per stream, so a fresh
-        # stream starts with cudaMalloc calls
         self.copy_stream = copy_stream if copy_stream is not None else torch.cuda.Stream()
+        # a long-lived loader passes its staging sets back in (BatchStream(..., staging=prev.staging))
+        self.staging = staging if staging is not None else [dict(bufs={}, done=None) for _ in range(self.depth + 1)]
 
-    def _issue(self, batch):
+    def _issue(self, batch, slot):
+        st = self.staging[slot]
+        out, nbytes = dict(batch), 0
         with torch.cuda.stream(self.copy_stream):
-            db, nb = to_device(batch, self.device, non_blocking=True)
+            if st["done"] is not None:
+                self.copy_stream.wait_event(st["done"])          # the batch that used this set has been computed
+            for k in _DEVICE_KEYS:
+                if k not in batch:
+                    continue
+                h = batch[k]
+                buf = st["bufs"].get(k)
+                if buf is None or buf.numel() < h.numel() or buf.dtype != h.dtype:
+                    buf = torch.empty((int(h.numel() * 1.25) + 16,), dtype=h.dtype, device=self.device)
+                    st["bufs"][k] = buf
+                view = buf[:h.numel()].view(h.shape)
+                view.copy_(h, non_blocking=True)
+                out[k] = view
+                nbytes += h.numel() * h.element_size()
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return db, nb, ev
+        return out, nbytes, ev, slot
 
     def __iter__(self):
         import collections
         it = iter(self.host_batches)
         q = collections.deque()
+        n_sets, nxt_slot = len(self.staging), 0
         for b in it:
-            q.append(self._issue(b))
-            if len(q) > self.depth:
+            q.append(self._issue(b, nxt_slot))
+            nxt_slot = (nxt_slot + 1) % n_sets
+            if len(q) >= self.depth:
                 break
         while q:
-            db, nb, ev = q.popleft()
+            db, nb, ev, slot = q.popleft()
             nxt = next(it, None)
             if nxt is not None:
-                q.append(self._issue(nxt))                      # overlaps the compute of `db`
+                q.append(self._issue(nxt, nxt_slot))            # overlaps the compute of `db`
+                nxt_slot = (nxt_slot + 1) % n_sets
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
-            for v in db.values():
-                if torch.is_tensor(v) and v.is_cuda:
-                    v.record_stream(cur)                        # allocated on the copy stream, consumed on `cur`
             yield db, nb
+            done = torch.cuda.Event()                           # the consumer is back: everything that reads `db` is queued
+            done.record(torch.cuda.current_stream())
+            self.staging[slot]["done"] = done
 
 
 class ResultFetcher(object):

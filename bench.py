@@ -78,6 +78,10 @@ def workload_config(args, extra=None):
                       "pipeline.forward_batch + pipeline.ResultFetcher (async D2H into pinned buffers); the L2 flush "
                       "write is inside the e2e region"}
     cfg.update(extra or {})
+    if cfg.get("mode") == "train":
+        cfg["workload"] = cfg["workload"].replace("inference", "training step").replace(
+            "UNet+pooling+ECC+affinity forward", "forward + MultiTaskLoss + backward + gradient all-reduce + AdamW")
+        cfg["e2e_api"] = "pipeline.to_device (H2D from pinned memory) + train.TrainStep + loss read back"
     return cfg
 
 
@@ -202,7 +206,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args, {"note": "reference CPU path (unmodified spconv CPU kernels, oracle/_ref) on "
                                                       "the host cores; each step covers %d of the batch's %d scene(s)"
                                                       % (n_sc, args.scenes), "scenes_per_step": n_sc,
-                                             "l2": "n/a (host)"}),
+                                             "l2": "n/a (host)", "e2e_api": "n/a (host path)"}),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -408,8 +412,8 @@ def run_ours(args, rank, world, local_rank):
         copies in and K reads out happen inside the timed region (the stream is created after the barrier, so the
         first copy is not overlapped with anything; the region ends when the last result has landed on the host)."""
         fetch = pipeline.ResultFetcher()
-        copy_stream = torch.cuda.Stream()                   # the loader's copy stream lives as long as the loader
-        for db, _ in pipeline.BatchStream((host[i % n_batches] for i in range(max(warmup, 2))), copy_stream=copy_stream):
+        warm = pipeline.BatchStream((host[i % n_batches] for i in range(max(warmup, 3))))   # a long-lived loader: its
+        for db, _ in warm:                                  # copy stream and staging buffers outlive the warm-up
             with torch.no_grad():
                 ret, _ = pipeline.forward_batch(net, db)
             fetch.fetch(ret)                                # pinned result buffers are allocated here, not in the region
@@ -420,7 +424,8 @@ def run_ours(args, rank, world, local_rank):
         flush.zero_()
         t0.record()
         prev = t0
-        for db, nb in pipeline.BatchStream((host[(warmup + i) % n_batches] for i in range(steps)), copy_stream=copy_stream):
+        for db, nb in pipeline.BatchStream((host[(warmup + i) % n_batches] for i in range(steps)),
+                                           copy_stream=warm.copy_stream, staging=warm.staging):
             with torch.no_grad():
                 ret, _ = pipeline.forward_batch(net, db)
             _, ob = fetch.fetch(ret)
@@ -525,7 +530,8 @@ def run_train_reference(args, rank):
     line = {"impl": "reference", "metric": TRAIN_METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": cb["steps"], "warmup": cb["warmup"], "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, {"mode": "train", "scenes_per_step": 1, "l2": "n/a (host)"}),
+            "config": dict(workload_config(args, {"mode": "train", "scenes_per_step": 1, "l2": "n/a (host)"}),
+                           e2e_api="n/a (host path)"),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)

@@ -1000,3 +1000,34 @@ def test_device_clustering_on_network_outputs_equals_host(W):
     assert np.array_equal(point_inst.cpu().numpy(), host_inst)
     assert np.array_equal(label.cpu().numpy(), hlabel)
     assert np.allclose(conf.cpu().numpy(), hconf, rtol=1e-5, atol=0)
+
+
+def test_batch_stream_and_result_fetcher_equal_the_direct_path(W):
+    """pipeline.BatchStream (H2D on a copy stream into persistent staging sets, overlapped with the previous batch's
+    compute) + ResultFetcher (async D2H into pinned buffers) give bit-identical results to to_device + forward_batch, for
+    batches of different sizes that recycle the staging sets, also when a second loader inherits the first one's sets."""
+    from wsis_b200 import pipeline, synthetic
+    net = pipeline.build_network(seed=123, device="cuda").eval()
+    sizes = [9000, 14000, 6000, 14000, 9000]
+    host = [pipeline.pin_batch(synthetic.collate([synthetic.make_scene(2100 + i, n_points=n)])) for i, n in enumerate(sizes)]
+    ref = []
+    for b in host:
+        with torch.no_grad():
+            ret, _ = pipeline.forward_batch(net, pipeline.to_device(b)[0])
+        ref.append({k: ret[k].cpu().clone() for k in ("edge_affinity", "sp_semantic_scores", "semantic_scores")})
+    fetch = pipeline.ResultFetcher(keys=("edge_affinity", "sp_semantic_scores"))
+    first = pipeline.BatchStream(host[:2])
+    got = []
+    for stream in (first, pipeline.BatchStream(host[2:], copy_stream=first.copy_stream, staging=first.staging)):
+        for db, nb in stream:
+            assert nb > 0
+            with torch.no_grad():
+                ret, _ = pipeline.forward_batch(net, db)
+            out, _ = fetch.fetch(ret)
+            fetch.wait()
+            got.append({"edge_affinity": out["edge_affinity"].clone(), "sp_semantic_scores": out["sp_semantic_scores"].clone(),
+                        "semantic_scores": ret["semantic_scores"].cpu()})
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        for k in b:
+            assert torch.equal(a[k], b[k]), k
