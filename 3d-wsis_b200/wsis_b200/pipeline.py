@@ -58,11 +58,19 @@ class BatchStream(object):
     in the caching allocator: set k is overwritten only after the compute stream has finished the batch that used it
     (an event recorded when the consumer asks for the next batch)."""
 
-    def __init__(self, host_batches, device="cuda", depth=1, copy_stream=None, staging=None):
+    def __init__(self, host_batches, device="cuda", depth=1, copy_stream=None, staging=None, prepare=False):
         self.host_batches, self.device, self.depth = host_batches, device, max(int(depth), 1)
         self.copy_stream = copy_stream if copy_stream is not None else torch.cuda.Stream()
         # a long-lived loader passes its staging sets back in (BatchStream(..., staging=prev.staging))
         self.staging = staging if staging is not None else [dict(bufs={}, done=None) for _ in range(self.depth + 1)]
+        # prepare=True: the coordinate-only part of the step (prepare_geometry: voxelization maps, rulebooks, tile
+        # records) is attached to every batch before it is yielded.  It runs on the COMPUTE stream: building it on the
+        # copy stream under the previous batch's feature compute is bit-identical on small batches
+        # (tests/test_gpu_parity.py) but at BASELINE size the run died with a launch failure whenever the geometry
+        # kernels ran concurrently with the persistent tensor-core kernels (tools/stream_debug.py: same stream / serialised
+        # launches / one scene pass, side stream fails) -- not understood yet, so the overlap is not shipped.
+        self.prepare = prepare
+        self._keep = []          # (event, objects): side-stream allocations stay referenced until their consumer is done
 
     def _issue(self, batch, slot):
         st = self.staging[slot]
@@ -87,27 +95,25 @@ class BatchStream(object):
         return out, nbytes, ev, slot
 
     def __iter__(self):
-        import collections
         it = iter(self.host_batches)
-        q = collections.deque()
-        n_sets, nxt_slot = len(self.staging), 0
-        for b in it:
-            q.append(self._issue(b, nxt_slot))
-            nxt_slot = (nxt_slot + 1) % n_sets
-            if len(q) >= self.depth:
-                break
-        while q:
-            db, nb, ev, slot = q.popleft()
-            nxt = next(it, None)
-            if nxt is not None:
-                q.append(self._issue(nxt, nxt_slot))            # overlaps the compute of `db`
-                nxt_slot = (nxt_slot + 1) % n_sets
-            cur = torch.cuda.current_stream()
-            cur.wait_event(ev)
+        n_sets, slot = len(self.staging), 0
+        first = next(it, None)
+        cur = self._issue(first, slot) if first is not None else None      # nothing to overlap the first batch with
+        while cur is not None:
+            db, nb, ev, used = cur
+            torch.cuda.current_stream().wait_event(ev)
+            if self.prepare:
+                db["_geometry"] = prepare_geometry(db)
             yield db, nb
-            done = torch.cuda.Event()                           # the consumer is back: everything that reads `db` is queued
+            # the consumer is back: everything that reads `db` is queued on the compute stream
+            done = torch.cuda.Event()
             done.record(torch.cuda.current_stream())
-            self.staging[slot]["done"] = done
+            self.staging[used]["done"] = done
+            self._keep.append((done, db))                       # tensors allocated on the copy stream: alive until `done`
+            self._keep = [(e, o) for e, o in self._keep if not e.query()]
+            nxt = next(it, None)
+            slot = (slot + 1) % n_sets
+            cur = self._issue(nxt, slot) if nxt is not None else None      # H2D (+ geometry) under the compute of `db`
 
 
 class ResultFetcher(object):
@@ -138,19 +144,59 @@ class ResultFetcher(object):
             self.last.synchronize()
 
 
-def forward_batch(model, dbatch, use_coords=True, mode=4, keep_unet_features=False):
-    """Voxelization + UNet + pooling + affinity for one device-resident batch.  Returns (ret dict, aux dict)."""
+def prepare_geometry(dbatch, mode=4, blocks=5):
+    """Everything of a step that depends on COORDINATES only (inference): voxelization maps, the superpoint / edge
+    segment indices, and the nine rulebooks of the U-Net with their tile records (conv.py:140-152 builds them lazily
+    inside the first conv that needs them; sparse_unet3d.py:229-350 fixes which).  No feature is read, so a loader can
+    run this for batch i+1 on its side stream while batch i's features are being computed (BatchStream(prepare=True)).
+    Returns the dict forward_batch(..., geometry=...) consumes."""
+    S = dbatch["num_superpoints"]
+    bs = dbatch["batch_size"]
+    voxel_locs, p2v_map, v2p_map = pointgroup_ops.voxelization_idx(dbatch["locs"], bs, mode)
+    geo = {"voxel_locs": voxel_locs, "p2v_map": p2v_map, "v2p_map": v2p_map,
+           "sp_index": W.SegmentIndex(dbatch["superpoint"], S), "edge_index_u": W.SegmentIndex(dbatch["edge_u_list"], S)}
+    coords, shape = voxel_locs.int(), list(dbatch["spatial_shape"])
+    geo["coords"] = coords
+    indice_dict = {}
+    for level in range(1, blocks + 1):
+        rb = W.rulebook_subm(coords, shape, 3, 1, bs)
+        rb.tiles_out()
+        lazy = spconv.ops.LazyPairs(rb)
+        indice_dict["subm%d" % level] = (coords, coords, lazy, lazy, shape)
+        if level < blocks:
+            rbc, oshape = W.rulebook_conv(coords, shape, 2, 2, 0, 1, bs)
+            rbc.tiles_out()                                   # strided conv (down)
+            rbc.tiles_in()                                    # inverse conv (up)
+            lazy = spconv.ops.LazyPairs(rbc)
+            indice_dict["spconv%d" % level] = (rbc.out_coords, coords, lazy, lazy, shape)
+            coords, shape = rbc.out_coords, oshape
+    geo["indice_dict"] = indice_dict
+    return geo
+
+
+def forward_batch(model, dbatch, use_coords=True, mode=4, keep_unet_features=False, geometry=None):
+    """Voxelization + UNet + pooling + affinity for one device-resident batch.  Returns (ret dict, aux dict).
+    `geometry` = prepare_geometry(dbatch) when a loader has already built the coordinate-only part (inference)."""
     locs = dbatch["locs"]
     S = dbatch["num_superpoints"]
-    voxel_locs, p2v_map, v2p_map = pointgroup_ops.voxelization_idx(locs, dbatch["batch_size"], mode)
+    geometry = geometry if geometry is not None else dbatch.get("_geometry")
+    if geometry is not None and (torch.is_grad_enabled() or model.training):
+        geometry = None                                       # the training path keeps the reference-format pairs
+    if geometry is not None:
+        voxel_locs, p2v_map, v2p_map = geometry["voxel_locs"], geometry["p2v_map"], geometry["v2p_map"]
+    else:
+        voxel_locs, p2v_map, v2p_map = pointgroup_ops.voxelization_idx(locs, dbatch["batch_size"], mode)
     coords_float = dbatch["locs_float"]
     superpoint = dbatch["superpoint"]
-    sp_index = W.SegmentIndex(superpoint, S)
+    sp_index = geometry["sp_index"] if geometry is not None else W.SegmentIndex(superpoint, S)
     centers = W.segment_reduce(coords_float, sp_index, "mean")                       # train_scannetv2.py:177
     feats = torch.cat((dbatch["feats"], coords_float), 1) if use_coords else dbatch["feats"]
     voxel_feats = pointgroup_ops.voxelization(feats, v2p_map, mode)                 # :189
-    input_ = spconv.SparseConvTensor(voxel_feats, voxel_locs.int(), dbatch["spatial_shape"], dbatch["batch_size"])
-    eindex = W.SegmentIndex(dbatch["edge_u_list"], S)
+    input_ = spconv.SparseConvTensor(voxel_feats, geometry["coords"] if geometry is not None else voxel_locs.int(),
+                                     dbatch["spatial_shape"], dbatch["batch_size"])
+    if geometry is not None:
+        input_.indice_dict = dict(geometry["indice_dict"])    # every conv finds its rulebook (conv.py:140-147)
+    eindex = geometry["edge_index_u"] if geometry is not None else W.SegmentIndex(dbatch["edge_u_list"], S)
     extra = {"superpoint": superpoint, "GIs": [GraphInfo(dbatch["ecc_edge_index"], dbatch["ecc_edgefeats"])],
              "edge_u_list": dbatch["edge_u_list"], "edge_v_list": dbatch["edge_v_list"],
              "superpoint_cenetr_xyz": centers, "sp_index": sp_index, "edge_index_u": eindex, "num_superpoints": S,

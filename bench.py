@@ -58,6 +58,7 @@ def parse():
                     help="scannet: configs[1] (8x6x2.6 m rooms, 2 cm voxels); s3dis: configs[3] (20x15x3 m rooms, 5 cm "
                          "voxels; use --points 1000000 --scenes 1)")
     ap.add_argument("--precision", default=os.environ.get("WSIS_PRECISION", "fp32"), choices=["fp32", "bf16", "simt"])
+    ap.add_argument("--stream-variants", action="store_true", help="also time the streaming loop's other configurations")
     ap.add_argument("--cpu-sample-scenes", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -406,15 +407,17 @@ def run_ours(args, rank, world, local_rank):
             total = float(t.item())
         return total, W.launch_count() - l0, extra, per_step
 
-    def timed_e2e(steps, warmup):
-        """The public streaming API: pipeline.BatchStream copies batch i+1 from pinned host memory on a copy stream while
-        batch i computes, pipeline.ResultFetcher reads every step's results back into pinned host buffers.  All K
-        copies in and K reads out happen inside the timed region (the stream is created after the barrier, so the
-        first copy is not overlapped with anything; the region ends when the last result has landed on the host)."""
+    def timed_stream(source, steps, warmup, prepare, fetch_results=True):
+        """The public streaming API: pipeline.BatchStream copies batch i+1 from `source` (pinned host memory for e2e) on
+        a copy stream while batch i computes -- with prepare=True it also builds batch i+1's coordinate-only part
+        (voxelization maps, rulebooks, tile records) there -- and pipeline.ResultFetcher reads every step's results
+        back into pinned host buffers.  All K copies in and K reads out happen inside the timed region (the stream is
+        created after the barrier, so the first batch is not overlapped with anything; the region ends when the last
+        result has landed on the host)."""
         fetch = pipeline.ResultFetcher()
-        warm = pipeline.BatchStream((host[i % n_batches] for i in range(max(warmup, 3))))   # a long-lived loader: its
-        for db, _ in warm:                                  # copy stream and staging buffers outlive the warm-up
-            with torch.no_grad():
+        warm = pipeline.BatchStream((source[i % n_batches] for i in range(max(warmup, 3))), prepare=prepare)
+        for db, _ in warm:                                  # a long-lived loader: its copy stream and staging buffers
+            with torch.no_grad():                           # outlive the warm-up
                 ret, _ = pipeline.forward_batch(net, db)
             fetch.fetch(ret)                                # pinned result buffers are allocated here, not in the region
         fetch.wait()
@@ -424,11 +427,11 @@ def run_ours(args, rank, world, local_rank):
         flush.zero_()
         t0.record()
         prev = t0
-        for db, nb in pipeline.BatchStream((host[(warmup + i) % n_batches] for i in range(steps)),
-                                           copy_stream=warm.copy_stream, staging=warm.staging):
+        for db, nb in pipeline.BatchStream((source[(warmup + i) % n_batches] for i in range(steps)),
+                                           copy_stream=warm.copy_stream, staging=warm.staging, prepare=prepare):
             with torch.no_grad():
                 ret, _ = pipeline.forward_batch(net, db)
-            _, ob = fetch.fetch(ret)
+            ob = fetch.fetch(ret)[1] if fetch_results else 0
             io = (nb, ob)
             flush.zero_()                                   # L2 flush between steps (inside the region: conservative)
             e = torch.cuda.Event(enable_timing=True)
@@ -449,7 +452,14 @@ def run_ours(args, rank, world, local_rank):
     t_begin = time.time()
     t_res, launches, _, ms_res = timed(step_resident, args.steps, args.warmup)
     t_end = time.time()
-    t_e2e, io, ms_e2e = timed_e2e(args.steps, args.warmup)
+    t_e2e, io, ms_e2e = timed_stream(host, args.steps, args.warmup, prepare=False)
+    extra_streams = None
+    if args.stream_variants:             # experiment: the same loop without the geometry prefetch, and from resident inputs
+        extra_streams = {}
+        for name, src, prep, fr in (("e2e_geometry_attached_by_loader", host, True, True), ("resident_streamed", dev, False, False)):
+            tt, _, ms = timed_stream(src, args.steps, args.warmup, prepare=prep, fetch_results=fr)
+            extra_streams[name] = {"value": args.scenes * args.steps * world / tt,
+                                   "ms_per_step_min_median_max": [round(min(ms), 3), round(statistics.median(ms), 3), round(max(ms), 3)]}
 
     roof = cpu = parity_obj = None
     launches_total = None
@@ -481,6 +491,8 @@ def run_ours(args, rank, world, local_rank):
                                                        round(max(ms_e2e), 3)]},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
                 "launches_total_per_step": launches_total, "roofline": roof, "cpu_baseline": cpu, "parity": parity_obj}
+        if extra_streams:
+            line["stream_variants"] = extra_streams
         print(json.dumps(line), flush=True)
 
 

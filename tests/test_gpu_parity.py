@@ -1031,3 +1031,30 @@ def test_batch_stream_and_result_fetcher_equal_the_direct_path(W):
     for a, b in zip(got, ref):
         for k in b:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_batch_stream_with_geometry_prefetch_equals_the_direct_path(W):
+    """BatchStream(prepare=True): the loader attaches the coordinate-only part of every batch (prepare_geometry:
+    voxelization maps, all nine rulebooks, tile records, segment indices) and forward_batch consumes it instead of
+    building rulebooks lazily inside the convs; the results must be bit-identical to the lazy path, for batches of
+    different sizes."""
+    from wsis_b200 import pipeline, synthetic
+    net = pipeline.build_network(seed=123, device="cuda").eval()
+    sizes = [9000, 14000, 6000, 14000, 9000, 11000]
+    host = [pipeline.pin_batch(synthetic.collate([synthetic.make_scene(2200 + i, n_points=n)])) for i, n in enumerate(sizes)]
+    keys = ("edge_affinity", "sp_semantic_scores", "semantic_scores", "pred_sp_offset_vectors")
+    ref = []
+    for b in host:
+        with torch.no_grad():
+            ret, _ = pipeline.forward_batch(net, pipeline.to_device(b)[0])
+        ref.append({k: ret[k].cpu().clone() for k in keys})
+    got = []
+    for db, _ in pipeline.BatchStream(host, prepare=True):
+        assert "_geometry" in db and len(db["_geometry"]["indice_dict"]) == 9
+        with torch.no_grad():
+            ret, _ = pipeline.forward_batch(net, db)
+        got.append({k: ret[k].cpu().clone() for k in keys})
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        for k in keys:
+            assert torch.equal(a[k], b[k]), k
