@@ -193,6 +193,30 @@ __global__ void __launch_bounds__(kTile) tile_record_kernel(const int32_t *__res
   }
 }
 
+// Records of the identity rulebook (K = 1, map[r] = r, natural order): what a 1x1 convolution looks like to conv_umma.
+// Same format as tile_record_kernel writes, without the hash set: slot r of tile t reads row t*128 + r.
+__global__ void __launch_bounds__(kTile) tile_record_identity_kernel(int64_t n, uint8_t *__restrict__ recs,
+                                                                     int32_t *__restrict__ uidx, int4 *__restrict__ meta,
+                                                                     int32_t *__restrict__ order, int32_t *__restrict__ stats) {
+  const int64_t t = blockIdx.x;
+  const int r = threadIdx.x, lane = r & 31, w = r >> 5;
+  const int64_t row = t * kTile + r;
+  const bool valid = row < n;
+  order[row] = valid ? (int32_t)row : -1;
+  uint8_t *rec = recs + t * (int64_t)rec_stride_bytes(1);
+  const uint32_t bal = __ballot_sync(0xffffffffu, valid);
+  if (lane == 0) reinterpret_cast<uint32_t *>(rec)[w] = bal;
+  const int nU = (int)min((int64_t)kTile, n - t * kTile);
+  uidx[t * kTile + r] = valid ? (int32_t)row : 0;
+  reinterpret_cast<uint16_t *>(rec + rec_hdr_bytes(1))[r] = valid ? (uint16_t)r : (uint16_t)0xFFFFu;
+  if (r < 32) reinterpret_cast<uint16_t *>(rec + 16 + 16)[r] = r == 0 ? (uint16_t)0xFF00u : (uint16_t)0xFFFFu;
+  if (r == 0) {
+    *reinterpret_cast<uint4 *>(rec + 16) = make_uint4((uint32_t)nU, 1u, (uint32_t)nU, 1u);
+    meta[t] = make_int4(rec_stride_bytes(1), nU, 1, nU);
+    if (t == 0) stats[0] = stats[1] = nU;          // most entries / most distinct rows of a tile (tile 0 is the fullest)
+  }
+}
+
 static int ilog2_ceil(int64_t v) {
   int b = 0;
   while (((int64_t)1 << b) < v) ++b;
@@ -247,6 +271,16 @@ int wsis_identity_order(int64_t N, int32_t *order, wsis_stream_t stream) {
   const int64_t n_pad = wsis_tile_pad(N);
   if (n_pad == 0) return 0;
   iota_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, as_stream(stream)>>>(order, N, n_pad);
+  WSIS_LAUNCH_OK();
+  return 0;
+}
+
+int wsis_tile_records_identity(int64_t n_rows, void *records, int32_t *uidx, int32_t *meta, int32_t *stats, int32_t *order,
+                               wsis_stream_t stream) {
+  const int64_t n_tiles = wsis_tile_pad(n_rows) / kTile;
+  if (n_tiles == 0) return 0;
+  tile_record_identity_kernel<<<(unsigned)n_tiles, kTile, 0, as_stream(stream)>>>(
+      n_rows, (uint8_t *)records, uidx, reinterpret_cast<int4 *>(meta), order, stats);
   WSIS_LAUNCH_OK();
   return 0;
 }

@@ -336,6 +336,15 @@ def _seq(seq, x):
     return x
 
 
+def _packed_of(module):
+    """Per-module cache of the pre-swizzled weight image (ops.PackedWeights)."""
+    pk = getattr(module, "_wsis_packed", None)
+    if pk is None:
+        pk = W.PackedWeights()
+        module._wsis_packed = pk
+    return pk
+
+
 def _head(norm_fn, width, out):
     return nn.Sequential(nn.Linear(width, width, bias=True), norm_fn(width), nn.ReLU(inplace=True),
                          nn.Linear(width, out))
@@ -445,7 +454,12 @@ class Network(nn.Module):
         ret['pred_sp_ins_size'] = _seq(self.sp_ins_size_head, ecc_outputs).squeeze(-1)
 
         centers = extra_data['superpoint_cenetr_xyz']
-        q, k, v = self.w_qs(ecc_outputs), self.w_ks(ecc_outputs), self.w_vs(ecc_outputs)
+        q = k = v = None
+        if fused:                                                                     # rows @ W^T on the tensor-core kernel
+            q, k, v = (W.dense_rows(ecc_outputs, lin.weight, packed=_packed_of(lin), holder=ecc_outputs, linear_layout=True)
+                       for lin in (self.w_qs, self.w_ks, self.w_vs))
+        if q is None or k is None or v is None:
+            q, k, v = self.w_qs(ecc_outputs), self.w_ks(ecc_outputs), self.w_vs(ecc_outputs)
         edge_u, edge_v = extra_data["edge_u_list"], extra_data["edge_v_list"]
         if fused:
             eseg = extra_data.get("edge_index_u") or W.SegmentIndex(edge_u, ecc_outputs.shape[0])

@@ -124,7 +124,22 @@ class TileMap:
     """A neighbour map in the form conv_umma consumes: destination rows in tiles of 128 along `order`, one
     record per tile (include/wsis_b200.h, wsis_tile_records)."""
 
-    def __init__(self, map_, n_dst, flip, order):
+    def __init__(self, map_, n_dst, flip, order, identity=False):
+        if identity:        # K = 1, map[r] = r: records written directly by wsis_tile_records_identity
+            dev = order
+            self.K, self.n_dst = 1, n_dst
+            self.num_tiles = lib().value("wsis_tile_pad", n_dst) // 128
+            self.stride = lib().value("wsis_tile_record_stride", 1)
+            self.ustride = lib().value("wsis_tile_unique_stride", 1)
+            self.order = torch.empty((max(self.num_tiles * 128, 1),), dtype=torch.int32, device=dev)
+            self.records = _bytes(self.num_tiles * self.stride, dev)
+            self.uidx = torch.empty((max(self.num_tiles * self.ustride, 4),), dtype=torch.int32, device=dev)
+            self.meta = torch.empty((max(self.num_tiles, 1), 4), dtype=torch.int32, device=dev)
+            self.stats = torch.empty((2,), dtype=torch.int32, device=dev)
+            if n_dst > 0:
+                lib().call("wsis_tile_records_identity", n_dst, _ptr(self.records), _ptr(self.uidx), _ptr(self.meta),
+                           _ptr(self.stats), _ptr(self.order), _stream())
+            return
         K = map_.shape[1]
         self.K, self.n_dst = K, n_dst
         self.order = order
@@ -403,6 +418,39 @@ def sparse_conv(src, weight3, map_, n_dst, flip, transpose_w=False, prologue=Non
         lib().call("wsis_conv_simt", _ptr(src), _ptr(map_), n_dst, K, int(flip), _ptr(weight3), int(transpose_w), Cin,
                    Cout, _ptr(scale), _ptr(shift), int(relu), _ptr(residual), _ptr(dst), _stream())
     return dst
+
+
+def _identity_tiles(n, device, holder=None):
+    """(map int32[n,1] = iota, TileMap) of the identity rulebook: what a 1x1 convolution / a Linear over rows looks
+    like to conv_umma.  Cached on `holder` (the coordinate tensor of the level) when given."""
+    cached = getattr(holder, "_wsis_ident", None) if holder is not None else None
+    if cached is not None and cached[0].shape[0] == n:
+        return cached
+    tiles = TileMap(None, n, 0, device, identity=True)
+    map_ = tiles.order[:n].view(n, 1)                     # the identity order doubles as the [n, 1] neighbour map
+    cached = (map_, tiles)
+    if holder is not None:
+        try:
+            holder._wsis_ident = cached
+        except Exception:  # noqa: BLE001
+            pass
+    return cached
+
+
+def dense_rows(src, weight, packed=None, holder=None, precision=None, linear_layout=False):
+    """src f32[n, Cin] @ W on the tensor-core conv kernel (a 1x1 submanifold conv is a sparse conv with the identity
+    rulebook: conv.py:113-119 does it with torch.mm).  weight f32[Cin, Cout], or the nn.Linear layout f32[Cout, Cin]
+    with linear_layout=True (y = x @ weight^T).  Returns None when the shape is not supported (the caller keeps its
+    library GEMM)."""
+    Cin, Cout = (weight.shape[1], weight.shape[0]) if linear_layout else weight.shape
+    precision = precision or _PRECISION
+    if precision == "simt" or not src.is_cuda or src.dtype != torch.float32 or src.shape[0] == 0 \
+            or not umma_supported(Cin, Cout):
+        return None
+    n = src.shape[0]
+    map_, tiles = _identity_tiles(n, src.device, holder)
+    return sparse_conv(src, weight.unsqueeze(0), map_, n, 0, bool(linear_layout), packed=packed, precision=precision,
+                       tiles=tiles)
 
 
 def sparse_conv_wgrad(src, map_, n_dst, flip, grad_out, K, Cin, Cout, prologue=None, order=None, precision=None):

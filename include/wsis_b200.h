@@ -142,6 +142,10 @@ int64_t wsis_tile_record_stride(int K);
 int64_t wsis_tile_unique_stride(int K);
 int wsis_tile_records(const int32_t *map, int64_t n_rows, int K, int flip, const int32_t *order, void *records,
                       int32_t *uidx, int32_t *meta, int32_t *stats, wsis_stream_t stream);
+/* Records of the identity rulebook (K = 1, map[r] = r, natural row order) -- a 1x1 convolution / a Linear over rows on
+ * wsis_conv_umma -- written directly (no hash set); `order` int32[wsis_tile_pad(n_rows)] receives the identity order. */
+int wsis_tile_records_identity(int64_t n_rows, void *records, int32_t *uidx, int32_t *meta, int32_t *stats, int32_t *order,
+                               wsis_stream_t stream);
 
 /* tcgen05 tensor-core path over tile records (num_tiles = wsis_tile_pad(n_dst)/128).  precision: 1 = bf16 operands
  * (1e-2 contract), 3 = bf16x3 split operands with fp32 accumulation in TMEM (1e-4 contract).

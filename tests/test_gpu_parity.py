@@ -1058,3 +1058,19 @@ def test_batch_stream_with_geometry_prefetch_equals_the_direct_path(W):
     for a, b in zip(got, ref):
         for k in keys:
             assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("n,cin,cout,linear", [(70001, 64, 32, False), (5000, 320, 160, False), (129, 128, 64, False),
+                                               (12345, 64, 64, True), (1, 64, 64, True)])
+def test_dense_rows_on_the_conv_kernel_matches_torch(W, n, cin, cout, linear):
+    """A 1x1 submanifold conv (conv.py:113-119: torch.mm) / a bias-free Linear over rows as a sparse conv with the identity
+    rulebook on the tensor-core kernel: within the fp32 contract of a float64 matmul."""
+    torch.manual_seed(n + cin)
+    x = torch.randn(n, cin, device="cuda")
+    w = torch.randn((cout, cin) if linear else (cin, cout), device="cuda") / cin ** 0.5
+    ref = (x.double() @ (w.double().t() if linear else w.double())).float()
+    holder = torch.empty(1, device="cuda")
+    for _ in range(2):                                       # second call: cached identity tiles and packed weights
+        got = W.dense_rows(x, w, packed=W.PackedWeights(), holder=holder, linear_layout=linear)
+        assert got is not None and rel(got.cpu().numpy(), ref.cpu().numpy()) < FP32_TOL
+    assert W.dense_rows(x, w, precision="simt", linear_layout=linear) is None
