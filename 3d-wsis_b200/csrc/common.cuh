@@ -49,6 +49,10 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
 
+// Host-mapped (zero-copy) word that a kernel fills right before it traps: a trap kills the context, device memory
+// becomes unreadable, but the host copy of this word still says WHICH wait gave up (wsis_debug_trap_word()).
+unsigned int *trap_word_device();   // device-visible address (NULL if the mapping could not be made)
+
 // ------------------------------------------------------------------------------------------------
 // coordinate hash: key = b:16 | x:16 | y:16 | z:16, open addressing with linear probing, slots = 2^m
 // ------------------------------------------------------------------------------------------------

@@ -88,7 +88,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // NANOSLEEP.SYNCS after a failed probe and the wake-up latency of a sleeping warp (on both sides of every stage hand-off)
 // dominated the pipeline's round trip.  A wait that has not completed after ~4 s is a protocol bug: report which
 // barrier and trap instead of hanging the device.
+__device__ unsigned int *d_trap_word = nullptr;   // host-mapped diagnostics record (common.cuh trap_word_device)
 __device__ __forceinline__ void mbar_deadlock(uint32_t bar, uint32_t parity) {
+  if (d_trap_word != nullptr) {
+    volatile unsigned int *w = d_trap_word;
+    w[1] = bar, w[2] = parity, w[3] = blockIdx.x, w[4] = threadIdx.x;
+    w[0] = 1u;
+    __threadfence_system();
+  }
   // no printf here: a device-side call would force the ABI on the kernel, and setmaxnreg needs a call-free kernel.
   // The trap surfaces as a launch failure on the next CUDA call; WSIS_CONV_DIAG builds report which barrier.
   (void)bar;
@@ -1205,6 +1212,14 @@ int wsis_conv_umma(const float *src, const void *records, const int32_t *uidx, c
   p.vec4 = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   p.num_tiles = num_tiles;
   int64_t smem = 0;
+  {
+    static bool trap_set = false;           // diagnostics only: one record per process
+    if (!trap_set) {
+      unsigned int *tw = trap_word_device();
+      cudaMemcpyToSymbol(wsis::umma::d_trap_word, &tw, sizeof(tw));
+      trap_set = true;
+    }
+  }
   if (plan_launch(p, K, Cin, Cout, NS, &smem)) return 1;
   p.diag = g_diag;
   {

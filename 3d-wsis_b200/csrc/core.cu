@@ -21,6 +21,21 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static unsigned int *g_trap_host = nullptr, *g_trap_dev = nullptr;
+
+unsigned int *trap_word_device() {
+  if (g_trap_dev == nullptr && g_trap_host == nullptr) {
+    if (cudaHostAlloc(reinterpret_cast<void **>(&g_trap_host), 64, cudaHostAllocMapped) == cudaSuccess) {
+      for (int i = 0; i < 16; ++i) g_trap_host[i] = 0;
+      if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&g_trap_dev), g_trap_host, 0) != cudaSuccess) g_trap_dev = nullptr;
+    } else {
+      cudaGetLastError();
+      g_trap_host = reinterpret_cast<unsigned int *>(1);   // do not retry
+    }
+  }
+  return g_trap_dev;
+}
+
 int sm_count() {
   // cached per device ordinal (one process may drive several GPUs)
   static std::atomic<int> cached[64];
@@ -215,6 +230,12 @@ __global__ void sort_scatter(const uint32_t *__restrict__ keys_in, const uint32_
 using namespace wsis;
 
 extern "C" {
+
+/* words written by a kernel that gave up on a barrier: [0] kernel id (1 conv_umma, 2 ecc_messages, 3 wgrad_umma,
+ * 4 bn_sync), [1] barrier shared-memory address, [2] parity / detail, [3] blockIdx.x; 0 = no trap recorded */
+int64_t wsis_debug_trap_word(int i) {
+  return (g_trap_host != nullptr && g_trap_host != reinterpret_cast<unsigned int *>(1) && i >= 0 && i < 16) ? (int64_t)g_trap_host[i] : -1;
+}
 
 int wsis_version(void) { return 100; }
 const char *wsis_last_error(void) { return g_err; }

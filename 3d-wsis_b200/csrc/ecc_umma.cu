@@ -41,6 +41,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ unsigned int *d_trap_word = nullptr;   // host-mapped diagnostics record (common.cuh trap_word_device)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   for (uint32_t n = 0; n < (1u << 24) && !ok; ++n) {
@@ -50,7 +51,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   }
-  if (!ok) __trap();
+  if (!ok) {
+    if (d_trap_word != nullptr) {
+      volatile unsigned int *w = d_trap_word;
+      w[1] = bar, w[2] = parity, w[3] = blockIdx.x, w[4] = threadIdx.x;
+      w[0] = 2u;
+      __threadfence_system();
+    }
+    __trap();
+  }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -252,6 +261,12 @@ ecc_messages_kernel(const uint8_t *__restrict__ he_packed, const uint8_t *__rest
     for (int q = 0; q < 4; ++q) {                          // unrolled: x[8 q + i] is a static register
       mbar_wait(barL, phL);                                // operands of this quarter have landed
       phL ^= 1;
+      // Every thread must have OBSERVED this phase of barL before thread 0 may start the next one: the next loads need
+      // nobody's participation, so a warp that is held up between the __syncthreads() below and this wait (co-resident
+      // CTAs of another stream) would otherwise find the barrier two phases ahead, read the parity as "not yet" and wait
+      // forever.  Warps 1-3 arrive (non-blocking, whole warps: named barriers count warps) here; warp 0 syncs on the
+      // same barrier, converged, right before its lane 0 issues the next loads.
+      if (warp != 0) asm volatile("bar.arrive 1, 128;" ::: "memory");
       if (warp == 0) {
         tc_fence_after();
         if (elect_one()) {
@@ -275,6 +290,10 @@ ecc_messages_kernel(const uint8_t *__restrict__ he_packed, const uint8_t *__rest
       mbar_wait(barM, phM);                                // D complete; sA (last quarter) and sW are free again
       phM ^= 1;
       tc_fence_after();
+      if (warp == 0) {                                     // all 4 warps have passed this quarter's barL wait
+        __syncwarp();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       if (tid == 0) {                                      // next operands stream in under the epilogue
         const int tn = t + gridDim.x;
         if (q < 3) {
@@ -345,6 +364,14 @@ int wsis_ecc_edge_mlp(const float *edgefeats, const int32_t *eorder, int64_t E, 
 int wsis_ecc_messages(const void *he_packed, const void *w4_packed, const float *b4, const float *h, const int64_t *src,
                       const int32_t *eorder, int64_t E, float *msg, wsis_stream_t stream) {
   if (E == 0) return 0;
+  {
+    static bool trap_set = false;
+    if (!trap_set) {
+      unsigned int *tw = trap_word_device();
+      cudaMemcpyToSymbol(eccu::d_trap_word, &tw, sizeof(tw));
+      trap_set = true;
+    }
+  }
   int tiles = (int)ceil_div(E, eccu::kTile);
   size_t smem = eccu::kATile + eccu::kWQuarter + sizeof(float) * eccu::kNF + 64 + 1024;
   WSIS_CUDA(cudaFuncSetAttribute(eccu::ecc_messages_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

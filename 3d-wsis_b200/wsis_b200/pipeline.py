@@ -64,11 +64,8 @@ class BatchStream(object):
         # a long-lived loader passes its staging sets back in (BatchStream(..., staging=prev.staging))
         self.staging = staging if staging is not None else [dict(bufs={}, done=None) for _ in range(self.depth + 1)]
         # prepare=True: the coordinate-only part of the step (prepare_geometry: voxelization maps, rulebooks, tile
-        # records) is attached to every batch before it is yielded.  It runs on the COMPUTE stream: building it on the
-        # copy stream under the previous batch's feature compute is bit-identical on small batches
-        # (tests/test_gpu_parity.py) but at BASELINE size the run died with a launch failure whenever the geometry
-        # kernels ran concurrently with the persistent tensor-core kernels (tools/stream_debug.py: same stream / serialised
-        # launches / one scene pass, side stream fails) -- not understood yet, so the overlap is not shipped.
+        # records) is built on the copy stream as well, i.e. under the previous batch's feature compute, and attached to
+        # the batch as "_geometry" (forward_batch consumes it)
         self.prepare = prepare
         self._keep = []          # (event, objects): side-stream allocations stay referenced until their consumer is done
 
@@ -90,6 +87,8 @@ class BatchStream(object):
                 view.copy_(h, non_blocking=True)
                 out[k] = view
                 nbytes += h.numel() * h.element_size()
+            if self.prepare:
+                out["_geometry"] = prepare_geometry(out)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         return out, nbytes, ev, slot
@@ -102,8 +101,6 @@ class BatchStream(object):
         while cur is not None:
             db, nb, ev, used = cur
             torch.cuda.current_stream().wait_event(ev)
-            if self.prepare:
-                db["_geometry"] = prepare_geometry(db)
             yield db, nb
             # the consumer is back: everything that reads `db` is queued on the compute stream
             done = torch.cuda.Event()

@@ -58,6 +58,8 @@ def parse():
                     help="scannet: configs[1] (8x6x2.6 m rooms, 2 cm voxels); s3dis: configs[3] (20x15x3 m rooms, 5 cm "
                          "voxels; use --points 1000000 --scenes 1)")
     ap.add_argument("--precision", default=os.environ.get("WSIS_PRECISION", "fp32"), choices=["fp32", "bf16", "simt"])
+    ap.add_argument("--no-geometry-prefetch", action="store_true",
+                    help="e2e without building the next batch's rulebooks / tile records on the loader's side stream")
     ap.add_argument("--stream-variants", action="store_true", help="also time the streaming loop's other configurations")
     ap.add_argument("--cpu-sample-scenes", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -75,9 +77,11 @@ def workload_config(args, extra=None):
     cfg = {"workload": what,
            "scenes_per_step": args.scenes, "points_per_scene": args.points, "weights": "random-init, seed 123",
            "l2": "flushed between timed steps (256 MiB write)",
-           "e2e_api": "pipeline.BatchStream (H2D of step i+1 from pinned memory on a copy stream under step i's compute) + "
+           "e2e_api": "pipeline.BatchStream (H2D of step i+1 from pinned memory%s on a side stream under step i's compute) + "
                       "pipeline.forward_batch + pipeline.ResultFetcher (async D2H into pinned buffers); the L2 flush "
-                      "write is inside the e2e region"}
+                      "write is inside the e2e region"
+                      % ("" if getattr(args, "no_geometry_prefetch", False) else
+                         " and step i+1's coordinate-only part (voxelization maps, rulebooks, tile records)")}
     cfg.update(extra or {})
     if cfg.get("mode") == "train":
         cfg["workload"] = cfg["workload"].replace("inference", "training step").replace(
@@ -463,11 +467,11 @@ def run_ours(args, rank, world, local_rank):
     t_begin = time.time()
     t_res, launches, _, ms_res = timed(step_resident, args.steps, args.warmup)
     t_end = time.time()
-    t_e2e, io, ms_e2e = timed_stream(host, args.steps, args.warmup, prepare=False)
+    t_e2e, io, ms_e2e = timed_stream(host, args.steps, args.warmup, prepare=not args.no_geometry_prefetch)
     extra_streams = None
     if args.stream_variants:             # experiment: the same loop without the geometry prefetch, and from resident inputs
         extra_streams = {}
-        for name, src, prep, fr in (("e2e_geometry_attached_by_loader", host, True, True), ("resident_streamed", dev, False, False)):
+        for name, src, prep, fr in (("e2e_no_geometry_prefetch", host, False, True), ("resident_pipelined", dev, True, False)):
             tt, _, ms = timed_stream(src, args.steps, args.warmup, prepare=prep, fetch_results=fr)
             extra_streams[name] = {"value": args.scenes * args.steps * world / tt,
                                    "ms_per_step_min_median_max": [round(min(ms), 3), round(statistics.median(ms), 3), round(max(ms), 3)]}

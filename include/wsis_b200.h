@@ -44,6 +44,10 @@ const char *wsis_last_error(void);
 int wsis_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t wsis_launch_count(void);
+/* diagnostics: word i (0..15) of the host-mapped record a kernel fills before it traps on a barrier wait that never
+ * completed ([0] kernel id: 1 conv_umma, 2 ecc_messages, 3 wgrad_umma; [1] barrier address; [2] parity; [3] CTA); the
+ * record survives the context failure.  -1 when unavailable. */
+int64_t wsis_debug_trap_word(int i);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* primitives: fill, exclusive scan, stable LSD radix sort (hand-written; replace torch::_unique's  */

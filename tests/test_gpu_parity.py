@@ -1034,10 +1034,11 @@ def test_batch_stream_and_result_fetcher_equal_the_direct_path(W):
 
 
 def test_batch_stream_with_geometry_prefetch_equals_the_direct_path(W):
-    """BatchStream(prepare=True): the loader attaches the coordinate-only part of every batch (prepare_geometry:
-    voxelization maps, all nine rulebooks, tile records, segment indices) and forward_batch consumes it instead of
-    building rulebooks lazily inside the convs; the results must be bit-identical to the lazy path, for batches of
-    different sizes."""
+    """BatchStream(prepare=True): the coordinate-only part of batch i+1 (prepare_geometry: voxelization maps, all nine
+    rulebooks, tile records, segment indices) is built on the loader's side stream while batch i computes, and
+    forward_batch consumes it instead of building rulebooks lazily inside the convs; the results must be bit-identical
+    to the lazy path, for batches of different sizes (the full-size version of this loop is tools/stream_debug.py: it
+    found a barrier phase-aliasing bug in ecc_messages_kernel that only co-resident CTAs of a second stream expose)."""
     from wsis_b200 import pipeline, synthetic
     net = pipeline.build_network(seed=123, device="cuda").eval()
     sizes = [9000, 14000, 6000, 14000, 9000, 11000]
