@@ -60,7 +60,9 @@ class BatchStream(object):
 
     def __init__(self, host_batches, device="cuda", depth=1, copy_stream=None, staging=None, prepare=False):
         self.host_batches, self.device, self.depth = host_batches, device, max(int(depth), 1)
-        self.copy_stream = copy_stream if copy_stream is not None else torch.cuda.Stream()
+        # high priority: the loader's small kernels (geometry build) must get SMs as the persistent conv CTAs of the
+        # compute stream retire, not after its whole queue has drained
+        self.copy_stream = copy_stream if copy_stream is not None else torch.cuda.Stream(priority=-1)
         # a long-lived loader passes its staging sets back in (BatchStream(..., staging=prev.staging))
         self.staging = staging if staging is not None else [dict(bufs={}, done=None) for _ in range(self.depth + 1)]
         # prepare=True: the coordinate-only part of the step (prepare_geometry: voxelization maps, rulebooks, tile

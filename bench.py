@@ -58,8 +58,9 @@ def parse():
                     help="scannet: configs[1] (8x6x2.6 m rooms, 2 cm voxels); s3dis: configs[3] (20x15x3 m rooms, 5 cm "
                          "voxels; use --points 1000000 --scenes 1)")
     ap.add_argument("--precision", default=os.environ.get("WSIS_PRECISION", "fp32"), choices=["fp32", "bf16", "simt"])
-    ap.add_argument("--no-geometry-prefetch", action="store_true",
-                    help="e2e without building the next batch's rulebooks / tile records on the loader's side stream")
+    ap.add_argument("--geometry-prefetch", action="store_true",
+                    help="value and e2e through the streaming loop that builds the next batch's rulebooks / tile records on "
+                         "the loader's side stream under the current batch's feature compute")
     ap.add_argument("--stream-variants", action="store_true", help="also time the streaming loop's other configurations")
     ap.add_argument("--cpu-sample-scenes", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -77,16 +78,21 @@ def workload_config(args, extra=None):
     cfg = {"workload": what,
            "scenes_per_step": args.scenes, "points_per_scene": args.points, "weights": "random-init, seed 123",
            "l2": "flushed between timed steps (256 MiB write)",
+           "value_api": ("the e2e loop over batches already resident in HBM (pipeline.BatchStream: the next step's "
+                         "coordinate-only part on the side stream under the current step's compute)"
+                         if getattr(args, "geometry_prefetch", False) else
+                         "pipeline.forward_batch on batches resident in HBM, steps issued one after the other on one stream"),
            "e2e_api": "pipeline.BatchStream (H2D of step i+1 from pinned memory%s on a side stream under step i's compute) + "
                       "pipeline.forward_batch + pipeline.ResultFetcher (async D2H into pinned buffers); the L2 flush "
                       "write is inside the e2e region"
-                      % ("" if getattr(args, "no_geometry_prefetch", False) else
-                         " and step i+1's coordinate-only part (voxelization maps, rulebooks, tile records)")}
+                      % (" and step i+1's coordinate-only part (voxelization maps, rulebooks, tile records)"
+                         if getattr(args, "geometry_prefetch", False) else "")}
     cfg.update(extra or {})
     if cfg.get("mode") == "train":
         cfg["workload"] = cfg["workload"].replace("inference", "training step").replace(
             "UNet+pooling+ECC+affinity forward", "forward + MultiTaskLoss + backward + gradient all-reduce + AdamW")
         cfg["e2e_api"] = "pipeline.to_device (H2D from pinned memory) + train.TrainStep + loss read back"
+        cfg["value_api"] = "train.TrainStep on batches resident in HBM, one stream"
     return cfg
 
 
@@ -211,7 +217,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args, {"note": "reference CPU path (unmodified spconv CPU kernels, oracle/_ref) on "
                                                       "the host cores; each step covers %d of the batch's %d scene(s)"
                                                       % (n_sc, args.scenes), "scenes_per_step": n_sc,
-                                             "l2": "n/a (host)", "e2e_api": "n/a (host path)"}),
+                                             "l2": "n/a (host)", "e2e_api": "n/a (host path)", "value_api": "n/a (host path)"}),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -429,13 +435,14 @@ def run_ours(args, rank, world, local_rank):
         created after the barrier, so the first batch is not overlapped with anything; the region ends when the last
         result has landed on the host)."""
         fetch = pipeline.ResultFetcher()
-        warm = pipeline.BatchStream((source[i % n_batches] for i in range(max(warmup, 3))), prepare=prepare)
+        warm = pipeline.BatchStream((source[i % n_batches] for i in range(max(warmup, 6))), prepare=prepare)
         for db, _ in warm:                                  # a long-lived loader: its copy stream and staging buffers
             with torch.no_grad():                           # outlive the warm-up
                 ret, _ = pipeline.forward_batch(net, db)
             fetch.fetch(ret)                                # pinned result buffers are allocated here, not in the region
         fetch.wait()
         barrier()
+        l0 = W.launch_count()
         evs, io = [], (0, 0)
         t0 = torch.cuda.Event(enable_timing=True)
         flush.zero_()
@@ -460,19 +467,31 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor([total], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total = float(t.item())
-        return total, io, per_step
+        return total, io, per_step, W.launch_count() - l0
 
+    # value: K steps over batches resident in HBM, issued one after the other on one stream.  With --geometry-prefetch
+    # both value and e2e run through the streaming loop whose side stream builds batch i+1's coordinate-only part under
+    # batch i's feature compute (median step 11.3 -> 10.0 ms in profiles/r02_bench_stream_variants.json); it is opt-in
+    # because single 20-65 ms stalls (the host thread blocks in the rulebook builder's output-count read-backs on the
+    # side stream) still show up in some 10-step runs.
+    prefetch = args.geometry_prefetch
     _quiesce_gc()
     clocks.wait_ready()
     t_begin = time.time()
-    t_res, launches, _, ms_res = timed(step_resident, args.steps, args.warmup)
+    if prefetch:
+        t_res, _, ms_res, launches = timed_stream(dev, args.steps, args.warmup, prepare=True, fetch_results=False)
+    else:
+        t_res, launches, _, ms_res = timed(step_resident, args.steps, args.warmup)
     t_end = time.time()
-    t_e2e, io, ms_e2e = timed_stream(host, args.steps, args.warmup, prepare=not args.no_geometry_prefetch)
+    t_seq, ms_seq = t_res, ms_res
+    if prefetch:
+        t_seq, _, _, ms_seq = timed(step_resident, args.steps, args.warmup)
+    t_e2e, io, ms_e2e, _ = timed_stream(host, args.steps, args.warmup, prepare=prefetch)
     extra_streams = None
     if args.stream_variants:             # experiment: the same loop without the geometry prefetch, and from resident inputs
         extra_streams = {}
-        for name, src, prep, fr in (("e2e_no_geometry_prefetch", host, False, True), ("resident_pipelined", dev, True, False)):
-            tt, _, ms = timed_stream(src, args.steps, args.warmup, prepare=prep, fetch_results=fr)
+        for name, src, prep, fr in (("e2e_geometry_prefetch", host, True, True), ("resident_geometry_prefetch", dev, True, False)):
+            tt, _, ms, _ = timed_stream(src, args.steps, args.warmup, prepare=prep, fetch_results=fr)
             extra_streams[name] = {"value": args.scenes * args.steps * world / tt,
                                    "ms_per_step_min_median_max": [round(min(ms), 3), round(statistics.median(ms), 3), round(max(ms), 3)]}
 
@@ -504,6 +523,10 @@ def run_ours(args, rank, world, local_rank):
                         "ms_per_step": 1e3 * t_e2e / args.steps,
                         "ms_per_step_min_median_max": [round(min(ms_e2e), 3), round(statistics.median(ms_e2e), 3),
                                                        round(max(ms_e2e), 3)]},
+                "single_stream": None if not prefetch else {"value": scenes / t_seq, "ms_per_step": 1e3 * t_seq / args.steps,
+                                  "ms_per_step_min_median_max": [round(min(ms_seq), 3), round(statistics.median(ms_seq), 3),
+                                                                 round(max(ms_seq), 3)],
+                                  "note": "the same K steps issued one after the other on one stream (resident inputs)"},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
                 "launches_total_per_step": launches_total, "roofline": roof, "cpu_baseline": cpu, "parity": parity_obj}
         if extra_streams:
@@ -558,7 +581,7 @@ def run_train_reference(args, rank):
             "steps": cb["steps"], "warmup": cb["warmup"], "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, {"mode": "train", "scenes_per_step": 1, "l2": "n/a (host)"}),
-                           e2e_api="n/a (host path)"),
+                           e2e_api="n/a (host path)", value_api="n/a (host path)"),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
