@@ -58,9 +58,10 @@ def parse():
                     help="scannet: configs[1] (8x6x2.6 m rooms, 2 cm voxels); s3dis: configs[3] (20x15x3 m rooms, 5 cm "
                          "voxels; use --points 1000000 --scenes 1)")
     ap.add_argument("--precision", default=os.environ.get("WSIS_PRECISION", "fp32"), choices=["fp32", "bf16", "simt"])
-    ap.add_argument("--geometry-prefetch", action="store_true",
-                    help="value and e2e through the streaming loop that builds the next batch's rulebooks / tile records on "
-                         "the loader's side stream under the current batch's feature compute")
+    ap.add_argument("--no-geometry-prefetch", action="store_true",
+                    help="value = steps issued one after the other on one stream, e2e = BatchStream without the geometry "
+                         "prefetch (default: both through the streaming loop whose side stream builds the next batch's "
+                         "voxelization maps / rulebooks / tile records under the current batch's feature compute)")
     ap.add_argument("--stream-variants", action="store_true", help="also time the streaming loop's other configurations")
     ap.add_argument("--cpu-sample-scenes", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -80,13 +81,13 @@ def workload_config(args, extra=None):
            "l2": "flushed between timed steps (256 MiB write)",
            "value_api": ("the e2e loop over batches already resident in HBM (pipeline.BatchStream: the next step's "
                          "coordinate-only part on the side stream under the current step's compute)"
-                         if getattr(args, "geometry_prefetch", False) else
+                         if not getattr(args, "no_geometry_prefetch", False) else
                          "pipeline.forward_batch on batches resident in HBM, steps issued one after the other on one stream"),
            "e2e_api": "pipeline.BatchStream (H2D of step i+1 from pinned memory%s on a side stream under step i's compute) + "
                       "pipeline.forward_batch + pipeline.ResultFetcher (async D2H into pinned buffers); the L2 flush "
                       "write is inside the e2e region"
-                      % (" and step i+1's coordinate-only part (voxelization maps, rulebooks, tile records)"
-                         if getattr(args, "geometry_prefetch", False) else "")}
+                      % ("" if getattr(args, "no_geometry_prefetch", False) else
+                         " and step i+1's coordinate-only part (voxelization maps, rulebooks, tile records)")}
     cfg.update(extra or {})
     if cfg.get("mode") == "train":
         cfg["workload"] = cfg["workload"].replace("inference", "training step").replace(
@@ -427,6 +428,8 @@ def run_ours(args, rank, world, local_rank):
             total = float(t.item())
         return total, W.launch_count() - l0, extra, per_step
 
+    loader = {"stream": None, "staging": None}
+
     def timed_stream(source, steps, warmup, prepare, fetch_results=True):
         """The public streaming API: pipeline.BatchStream copies batch i+1 from `source` (pinned host memory for e2e) on
         a copy stream while batch i computes -- with prepare=True it also builds batch i+1's coordinate-only part
@@ -435,7 +438,11 @@ def run_ours(args, rank, world, local_rank):
         created after the barrier, so the first batch is not overlapped with anything; the region ends when the last
         result has landed on the host)."""
         fetch = pipeline.ResultFetcher()
-        warm = pipeline.BatchStream((source[i % n_batches] for i in range(max(warmup, 6))), prepare=prepare)
+        # one loader for the whole process: its side stream (and with it the allocator pool the geometry tensors come
+        # from) and its staging sets are created once and outlive every loop
+        warm = pipeline.BatchStream((source[i % n_batches] for i in range(max(warmup, 6))), prepare=prepare,
+                                    copy_stream=loader["stream"], staging=loader["staging"])
+        loader["stream"], loader["staging"] = warm.copy_stream, warm.staging
         for db, _ in warm:                                  # a long-lived loader: its copy stream and staging buffers
             with torch.no_grad():                           # outlive the warm-up
                 ret, _ = pipeline.forward_batch(net, db)
@@ -469,12 +476,16 @@ def run_ours(args, rank, world, local_rank):
             total = float(t.item())
         return total, io, per_step, W.launch_count() - l0
 
-    # value: K steps over batches resident in HBM, issued one after the other on one stream.  With --geometry-prefetch
-    # both value and e2e run through the streaming loop whose side stream builds batch i+1's coordinate-only part under
-    # batch i's feature compute (median step 11.3 -> 10.0 ms in profiles/r02_bench_stream_variants.json); it is opt-in
-    # because single 20-65 ms stalls (the host thread blocks in the rulebook builder's output-count read-backs on the
-    # side stream) still show up in some 10-step runs.
-    prefetch = args.geometry_prefetch
+    # value and e2e run through the public streaming loop (pipeline.BatchStream): the loader's high-priority side stream
+    # builds batch i+1's coordinate-only part (voxelization maps, rulebooks, tile records: no feature is read) under
+    # batch i's feature compute; value feeds it batches that are already resident in HBM, e2e pinned host batches.
+    # `single_stream` = the same K resident steps issued one after the other on one stream (what --no-geometry-prefetch
+    # reports as value).
+    prefetch = not args.no_geometry_prefetch
+    if prefetch:
+        # set-up, not measurement: the loader's side stream has its own allocator pool; an untimed pass maps it (growing
+        # it inside the first timed loop showed up as single 25-75 ms steps)
+        timed_stream(dev, 8, 3, prepare=True, fetch_results=False)
     _quiesce_gc()
     clocks.wait_ready()
     t_begin = time.time()
@@ -490,7 +501,7 @@ def run_ours(args, rank, world, local_rank):
     extra_streams = None
     if args.stream_variants:             # experiment: the same loop without the geometry prefetch, and from resident inputs
         extra_streams = {}
-        for name, src, prep, fr in (("e2e_geometry_prefetch", host, True, True), ("resident_geometry_prefetch", dev, True, False)):
+        for name, src, prep, fr in (("e2e_no_geometry_prefetch", host, False, True), ("resident_stream_no_geometry_prefetch", dev, False, False)):
             tt, _, ms, _ = timed_stream(src, args.steps, args.warmup, prepare=prep, fetch_results=fr)
             extra_streams[name] = {"value": args.scenes * args.steps * world / tt,
                                    "ms_per_step_min_median_max": [round(min(ms), 3), round(statistics.median(ms), 3), round(max(ms), 3)]}
