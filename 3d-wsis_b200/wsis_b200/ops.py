@@ -566,6 +566,17 @@ class SegmentIndex:
         lib().call("wsis_segment_csr", _ptr(ids), self.n, self.S, _ptr(self.order), _ptr(self.offsets), _ptr(ws),
                    _stream())
 
+    def validate(self):
+        """Raises if an id lies outside [0, S): the CSR kernel clamps such ids into the first / last segment instead of
+        corrupting memory, which would silently merge foreign rows into that segment's reduction (a wrong
+        `num_superpoints` in a batch dict).  One host sync: for set-up code and the torch_scatter drop-in, not for the
+        per-step path."""
+        if self.n:
+            lo, hi = int(self.ids.min().item()), int(self.ids.max().item())
+            if lo < 0 or hi >= self.S:
+                raise RuntimeError("wsis_b200: segment ids span [%d, %d] but num_segments is %d" % (lo, hi, self.S))
+        return self
+
 
 _REDUCE = {"sum": 0, "add": 0, "mean": 1, "max": 2}
 
@@ -591,7 +602,10 @@ def scatter(src, index, dim=0, reduce="sum", dim_size=None):
     assert dim == 0
     if dim_size is None:
         dim_size = int(index.max().item()) + 1 if index.numel() > 0 else 0
-    return segment_reduce(src, SegmentIndex(index, dim_size), reduce)
+        if index.numel() > 0 and int(index.min().item()) < 0:
+            raise RuntimeError("wsis_b200: scatter index must be non-negative")
+        return segment_reduce(src, SegmentIndex(index, dim_size), reduce)
+    return segment_reduce(src, SegmentIndex(index, dim_size).validate(), reduce)    # like torch_scatter: bad ids raise
 
 
 def gather_rows(src, idx):

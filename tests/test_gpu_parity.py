@@ -1075,3 +1075,14 @@ def test_dense_rows_on_the_conv_kernel_matches_torch(W, n, cin, cout, linear):
         got = W.dense_rows(x, w, packed=W.PackedWeights(), holder=holder, linear_layout=linear)
         assert got is not None and rel(got.cpu().numpy(), ref.cpu().numpy()) < FP32_TOL
     assert W.dense_rows(x, w, precision="simt", linear_layout=linear) is None
+
+
+def test_segment_index_validation_raises_on_out_of_range_ids(W):
+    """A wrong segment count must not silently merge rows into the last segment (torch_scatter raises too)."""
+    ids = cu(np.array([0, 1, 5, 2], dtype=np.int64))
+    x = cu(np.ones((4, 3), np.float32))
+    with pytest.raises(RuntimeError):
+        W.scatter(x, ids, reduce="sum", dim_size=4)
+    with pytest.raises(RuntimeError):
+        W.SegmentIndex(ids, 3).validate()
+    assert W.scatter(x, ids, reduce="sum", dim_size=6).shape == (6, 3)
