@@ -737,3 +737,24 @@ def test_vectorised_loss_matches_reference_golden(golden_dir, tag, epoch):
             assert t[k].grad is None or float(t[k].grad.abs().max()) == 0.0
         else:
             assert np.abs(t[k].grad.numpy() - ref).max() < 1e-5 * max(np.abs(ref).max(), 1e-12), k
+
+
+def test_small_tcgen05_kernels_barrier_protocol_models():
+    """tools/protocol_model.py also transcribes the mbarrier protocols of ecc_messages_kernel (csrc/ecc_umma.cu) and
+    wgrad_umma_kernel (csrc/wgrad_umma.cu).  The first ecc_messages protocol let thread 0 start the next operand load
+    before every warp had tested the barrier for the current one: under random schedules a held-up warp finds the barrier
+    two phases ahead and waits forever (on the GPU: a watchdog trap, but only with CTAs of a second stream co-resident on
+    the SM).  The model must catch that protocol and pass the shipped ones."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import protocol_model as pm
+    for seed in range(150):
+        assert pm.EccMessagesCta(16, fixed=True).run(seed)
+        assert pm.WgradCta(14, warps=4).run(seed)
+        assert pm.WgradCta(3, warps=16).run(seed)
+    caught = 0
+    for seed in range(60):
+        try:
+            pm.EccMessagesCta(16, fixed=False).run(seed)
+        except pm.ProtocolError:
+            caught += 1
+    assert caught >= 5, caught

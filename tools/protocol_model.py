@@ -232,6 +232,155 @@ class Cta(object):
         return tuple((b.phase, b.pending) for b in bars) + (len(self.done_stages),)
 
 
+class CtaBarrier(object):
+    """__syncthreads() / a named barrier among `count` warps: arrive, then wait for the generation to complete."""
+
+    def __init__(self, count):
+        self.count, self.pending, self.gen = count, count, 0
+
+    def arrive(self):
+        g = self.gen
+        self.pending -= 1
+        if self.pending == 0:
+            self.pending, self.gen = self.count, self.gen + 1
+        return g
+
+    def done(self, g):
+        return self.gen > g
+
+
+class SmallKernelModel(object):
+    """Random-schedule runner shared by the two small tcgen05 kernels below: `roles` are generators, `engines` model the
+    asynchronous units (TMA bulk copies, the tensor core) that arrive on an mbarrier some time after they were started."""
+
+    def _run(self, roles, state, seed, max_steps=10 ** 6):
+        rng = random.Random(seed)
+        alive = list(range(len(roles)))
+        idle = 0
+        for _ in range(max_steps):
+            if not alive:
+                return True
+            i = rng.choice(alive)
+            before = state()
+            try:
+                next(roles[i])
+            except StopIteration:
+                alive.remove(i)
+                idle = 0
+                continue
+            idle = idle + 1 if state() == before else 0
+            if idle > 400 * len(roles):
+                raise ProtocolError("deadlock: no role makes progress")
+        raise ProtocolError("step budget exhausted")
+
+
+class EccMessagesCta(SmallKernelModel):
+    """ecc_messages_kernel (csrc/ecc_umma.cu): 4 warps; per (tile, quarter) every warp waits for the operand load (barL),
+    warp 0 issues the MMAs, every warp waits for them (barM), thread 0 starts the NEXT load, all warps run the epilogue and
+    meet at __syncthreads().  `fixed=False` is the protocol as first written: the next load is started as soon as warp 0
+    has seen barM, although a slower warp may not have tested barL for the CURRENT quarter yet -- the load needs nobody's
+    participation, so barL can run two phases ahead of that warp, whose parity test then never passes.  `fixed=True`:
+    warps 1-3 arrive on a named barrier after their barL wait and warp 0 syncs on it before it starts the next load."""
+
+    def __init__(self, quarters, fixed):
+        self.Q, self.fixed = quarters, fixed
+        self.barL, self.barM = Barrier(1), Barrier(1)
+        self.cta, self.named = CtaBarrier(4), CtaBarrier(4)
+        self.loads, self.mmas = [], []          # started, not yet completed
+        self.seen = [0, 0, 0, 0]
+
+    def engine(self, queue, bar):
+        while True:
+            if queue:
+                yield                               # the unit takes a while
+                queue.pop(0)
+                bar.arrive()
+            if self.finished:
+                return
+            yield
+
+    def warp(self, w):
+        phL = phM = 0
+        for k in range(self.Q):
+            yield from wait(self.barL, phL, k + 1, "warp %d operands of quarter %d" % (w, k))
+            phL ^= 1
+            self.seen[w] = k + 1
+            g_named = self.named.arrive() if self.fixed and w != 0 else None
+            if w == 0:
+                self.mmas.append(k)
+            yield
+            yield from wait(self.barM, phM, k + 1, "warp %d accumulator of quarter %d" % (w, k))
+            phM ^= 1
+            if w == 0:
+                if self.fixed:
+                    g_named = self.named.arrive()
+                    while not self.named.done(g_named):
+                        yield
+                if k + 1 < self.Q:
+                    self.loads.append(k + 1)       # needs nobody's participation
+            yield                                   # epilogue
+            g = self.cta.arrive()
+            while not self.cta.done(g):
+                yield
+        self.done_warps += 1
+        if self.done_warps == 4:
+            self.finished = True
+
+    def run(self, seed=0):
+        self.finished, self.done_warps = False, 0
+        self.loads.append(0)
+        roles = [self.warp(w) for w in range(4)] + [self.engine(self.loads, self.barL), self.engine(self.mmas, self.barM)]
+        return self._run(roles, lambda: (self.barL.phase, self.barM.phase, self.cta.gen, self.named.gen, tuple(self.seen),
+                                         len(self.loads), len(self.mmas), self.done_warps), seed)
+
+
+class WgradCta(SmallKernelModel):
+    """wgrad_umma_kernel (csrc/wgrad_umma.cu): 16 warps, two operand buffers; before group `it` is gathered into buffer
+    it & 1 every warp waits for the commit of group it - 2 (parity ((it >> 1) - 1) & 1), then gathers, __syncthreads(),
+    warp 0 issues the group's MMAs and commits to the buffer's barrier."""
+
+    def __init__(self, groups, warps=4):
+        self.G, self.W = groups, warps
+        self.bar = [Barrier(1), Barrier(1)]
+        self.cta = CtaBarrier(warps)
+        self.mmas = [[], []]
+        self.buf = [None, None]
+
+    def engine(self, b):
+        while True:
+            if self.mmas[b]:
+                yield
+                it = self.mmas[b].pop(0)
+                if self.buf[b] != it:
+                    raise ProtocolError("MMAs of group %d read buffer %d holding group %s" % (it, b, self.buf[b]))
+                self.bar[b].arrive()
+            if self.finished:
+                return
+            yield
+
+    def warp(self, w):
+        for it in range(self.G):
+            b = it & 1
+            if it >= 2:
+                yield from wait(self.bar[b], ((it >> 1) - 1) & 1, it >> 1, "warp %d buffer %d before group %d" % (w, b, it))
+            self.buf[b] = it                        # gather: overwrite the operand buffer
+            yield
+            g = self.cta.arrive()
+            while not self.cta.done(g):
+                yield
+            if w == 0:
+                self.mmas[b].append(it)
+        self.done_warps += 1
+        if self.done_warps == self.W:
+            self.finished = True
+
+    def run(self, seed=0):
+        self.finished, self.done_warps = False, 0
+        roles = [self.warp(w) for w in range(self.W)] + [self.engine(0), self.engine(1)]
+        return self._run(roles, lambda: (self.bar[0].phase, self.bar[1].phase, self.cta.gen, len(self.mmas[0]),
+                                         len(self.mmas[1]), self.done_warps), seed)
+
+
 def random_tiles(rng, n_tiles, max_units=27, max_kb=3):
     return [(rng.randint(1, max_units), rng.randint(1, max_kb)) for _ in range(n_tiles)]
 
@@ -242,7 +391,16 @@ if __name__ == "__main__":
                                               (8, 2, 2, 1, 1, False, 1), (4, 1, 2, 4, 2, False, 2), (2, 2, 2, 2, 2, False, 4)):
         for seed in range(20):
             Cta(random_tiles(r, 6), na, nrc, 2, nbg, nmma, nbuf=nbuf, resident=res, us=us).run(seed)
-    print("protocol ok")
+    for seed in range(100):
+        EccMessagesCta(12, fixed=True).run(seed)
+        WgradCta(14).run(seed)
+    caught = 0
+    for seed in range(100):
+        try:
+            EccMessagesCta(12, fixed=False).run(seed)
+        except ProtocolError:
+            caught += 1
+    print("protocol ok; the first ecc_messages protocol deadlocks under %d of 100 random schedules" % caught)
     try:  # four issuers on a two-stage ring: an issuer's next stage is two generations ahead on the same buffer
         for seed in range(50):
             Cta(random_tiles(r, 6), 2, 2, 2, 2, 4).run(seed)
