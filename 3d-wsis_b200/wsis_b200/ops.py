@@ -7,6 +7,7 @@ in this file computes on the CPU; a CPU tensor where a CUDA tensor is required r
 import ctypes
 import math
 import os
+import weakref
 
 import torch
 
@@ -187,30 +188,22 @@ class Rulebook:
         # rulebook lives as long as indice_dict holds the pairs); the way back is WEAK: a strong one would make every
         # rulebook of every step (pairs [K,2,N] = 117 MB at level 1, tile records, maps) a reference cycle that only the
         # cyclic collector frees -- in training that showed up as GBs of dead rulebooks and 100-380 ms allocator stalls.
-        cached = self._pairs
-        if cached is not None and not isinstance(cached, tuple):
-            cached = tuple(r() for r in cached)
-            if any(t is None for t in cached):
-                cached = None
-        if cached is not None:
-            return cached
-        self._pairs = None
-        if self._pairs is None:
-            dev = self.nbr_in.device
-            N, K = self.n_in, self.K
-            pairs = torch.empty((K, 2, N), dtype=torch.int32, device=dev)
-            num = torch.empty((K,), dtype=torch.int32, device=dev)
-            if N > 0:
-                pos = torch.empty((K * N + 1,), dtype=torch.int32, device=dev)
-                ws = _bytes(lib().value("wsis_scan_ws_bytes", K * N), dev)
-                lib().call("wsis_pairs_from_nbr", _ptr(self.nbr_in), N, K, _ptr(pairs), _ptr(num), _ptr(pos), _ptr(ws),
-                           _stream())
-            else:
-                num.zero_()
-            import weakref
-            self._pairs = [weakref.ref(pairs), weakref.ref(num)]
-            return pairs, num
-        return self._pairs
+        if self._pairs is not None:
+            cached = tuple(r() for r in self._pairs)
+            if all(t is not None for t in cached):
+                return cached
+        dev = self.nbr_in.device
+        N, K = self.n_in, self.K
+        pairs = torch.empty((K, 2, N), dtype=torch.int32, device=dev)
+        num = torch.empty((K,), dtype=torch.int32, device=dev)
+        if N > 0:
+            pos = torch.empty((K * N + 1,), dtype=torch.int32, device=dev)
+            ws = _bytes(lib().value("wsis_scan_ws_bytes", K * N), dev)
+            lib().call("wsis_pairs_from_nbr", _ptr(self.nbr_in), N, K, _ptr(pairs), _ptr(num), _ptr(pos), _ptr(ws), _stream())
+        else:
+            num.zero_()
+        self._pairs = [weakref.ref(pairs), weakref.ref(num)]
+        return pairs, num
 
     # (map, flip) for: y[dst] = sum_k x[map[dst,k]] W[k]
     def fwd_map(self):
@@ -339,7 +332,6 @@ def rulebook_from_pairs(pairs, num, n_in, n_out, subm):
         nbr_out = torch.full((n_out, K), -1, dtype=torch.int32, device=dev)
         lib().call("wsis_nbr_from_pairs", _ptr(pairs), _ptr(num), stride, K, 1, _ptr(nbr_out), _stream())
     rb = Rulebook("subm" if subm else "conv", K, n_in, n_out, nbr_in, nbr_out, None)
-    import weakref
     rb._pairs = [weakref.ref(pairs), weakref.ref(num)]     # weak: the caller's pairs tensor points back at `rb`
     return rb
 

@@ -14,7 +14,6 @@ What is different from running the reference's modules under autograd:
     1/world average, the ECC gradient clamp (train_scannetv2.py:246-249) and AdamW run as one kernel over the flat
     parameter buffer (`wsis_adamw_step`).
 """
-import math
 import os
 
 import torch
@@ -502,4 +501,5 @@ def loss_inputs(ret, dbatch):
     }
 
 
-__all__ = ["TrainStep", "FlatAdamW", "MultiTaskLoss", "bn_relu_conv", "batch_norm_train", "run_sequential", "math"]
+__all__ = ["TrainStep", "FlatAdamW", "MultiTaskLoss", "bn_relu_conv", "batch_norm_train", "run_sequential", "ce_dice_loss",
+           "gather_rows", "segment_mean", "loss_inputs"]

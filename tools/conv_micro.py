@@ -84,8 +84,9 @@ def sweep(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", action="store_true", help="BASELINE.json configs[4] sweep (one JSON line per case)")
-    ap.add_argument("--sweep-voxels", default="50000,200000,500000,1000000,2000000")
-    ap.add_argument("--sweep-density", default="0.02,0.1,0.3,surface")
+    ap.add_argument("--sweep-voxels", default="50000,150000,500000,1000000,2000000")
+    ap.add_argument("--sweep-density", default="0.01,0.1,0.3,surface,1.0",
+                    help="occupancy of a cube (1.0 = solid blob, ~27 pairs/voxel; 0.01 = random scatter, ~1.3) or `surface`")
     ap.add_argument("--sweep-channels", default="16,32,48,64")
     ap.add_argument("--scenes", type=int, default=4)
     ap.add_argument("--points", type=int, default=150000)
