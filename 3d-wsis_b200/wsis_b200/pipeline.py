@@ -143,6 +143,12 @@ class ResultFetcher(object):
             self.last.synchronize()
 
 
+def unet_rulebook_keys(blocks=5):
+    """The `indice_key`s the U-Net's convolutions look their rulebooks up by (sparse_unet3d.py:229-350, backbone_3D_WSIS.py:
+    46-50): one submanifold rulebook per level, one strided rulebook per down / up pair."""
+    return ["subm%d" % level for level in range(1, blocks + 1)] + ["spconv%d" % level for level in range(1, blocks)]
+
+
 def prepare_geometry(dbatch, mode=4, blocks=5):
     """Everything of a step that depends on COORDINATES only (inference): voxelization maps, the superpoint / edge
     segment indices, and the nine rulebooks of the U-Net with their tile records (conv.py:140-152 builds them lazily
@@ -169,6 +175,7 @@ def prepare_geometry(dbatch, mode=4, blocks=5):
             lazy = spconv.ops.LazyPairs(rbc)
             indice_dict["spconv%d" % level] = (rbc.out_coords, coords, lazy, lazy, shape)
             coords, shape = rbc.out_coords, oshape
+    assert sorted(indice_dict) == sorted(unet_rulebook_keys(blocks))
     geo["indice_dict"] = indice_dict
     return geo
 

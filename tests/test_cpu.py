@@ -758,3 +758,14 @@ def test_small_tcgen05_kernels_barrier_protocol_models():
         except pm.ProtocolError:
             caught += 1
     assert caught >= 5, caught
+
+
+def test_prepared_geometry_keys_match_the_network():
+    """pipeline.prepare_geometry pre-builds the rulebooks under the `indice_key`s the network's convolutions ask for
+    (conv.py:140-147): every sparse conv of the mirror network (3x3 / strided / inverse; the 1x1 shortcuts have no
+    rulebook) must find its key in that list, and no listed key may be unused."""
+    import spconv
+    from wsis_b200 import pipeline
+    net = pipeline.build_network(seed=1, device="cpu")
+    used = {m.indice_key for m in net.modules() if isinstance(m, spconv.conv.SparseConvolution) and not m.conv1x1}
+    assert used == set(pipeline.unet_rulebook_keys(pipeline.DEFAULT_MODEL_CFG["blocks"]))
